@@ -1,0 +1,153 @@
+/* svgb200 — C ABI of the B200-native sparse video-DiT attention engine.
+ *
+ * The reference (svg-project/Sparse-VideoGen) has no FFI on this path: its boundary is the set of
+ * Python operator signatures imported by svg/models/<m>/attention.py (hyvideo/attention.py:12-28)
+ * and the svg/kernels/ops API.  This header is the boundary our own Python shim binds with ctypes;
+ * each entry point names the reference operator it stands behind.  INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no torch types.
+ *   - every function returns 0 on success, <0 on error; svgb_last_error() returns a thread-local
+ *     message for the last failure on the calling thread.
+ *   - all data pointers are DEVICE pointers unless a parameter is documented "host".
+ *   - no function allocates device memory or synchronises the device: the caller provides the
+ *     workspace (sizes from the *_bytes queries) and the cudaStream_t (passed as void*).
+ *   - integer outputs (labels, permutations, plans, maps) are bit-exact, deterministic.
+ *   - dtype: SVGB_BF16 or SVGB_F16 for q/k/v/o.
+ */
+#ifndef SVGB200_H_
+#define SVGB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SVGB_BF16 0
+#define SVGB_F16 1
+
+/* element-mask families for the SVG1 band plan (reference generate_temporal_head_mask_mod) */
+#define SVGB_MASK_NONE 0
+#define SVGB_MASK_HY 1  /* hyvideo/utils.py:20-44  m0=F*P, m1=F*P+prompt_len, m2=W              */
+#define SVGB_MASK_WAN 2 /* wan/utils.py:25-41      m0=P (first-frame sink), m2=W  (|q-kv| <= W) */
+#define SVGB_MASK_COG 3 /* cog/utils.py:30-46      m0=first-col limit, m1=prompt_len, m2=W      */
+
+/* ---- library ---------------------------------------------------------------------------- */
+int svgb_version(void);
+const char* svgb_last_error(void);
+/* 0 iff the current CUDA device is sm_100 (B200); fills optional outputs */
+int svgb_device_check(int* sm_major, int* sm_minor, int* num_sms);
+
+/* ---- attention plans -------------------------------------------------------------------- */
+/* Host-side descriptor of a device-resident plan (filled by the plan functions, read by
+ * svgb_attn_fwd).  Plain data; copyable. */
+typedef struct svgb_plan {
+  int32_t kind;          /* 1 = variable-block, 2 = band */
+  int32_t BH, S;
+  int32_t max_items;     /* grid.x of the attention launch */
+  int32_t items_stride;  /* 0 when one plan serves every head */
+  int32_t counts_stride;
+  int32_t mask_mode, m0, m1, m2;
+  int64_t counts_off, items_off, chunks_off; /* byte offsets inside the plan workspace */
+  int64_t bytes;
+} svgb_plan;
+
+/* SVG2 / BSR / dense: q-block i of head h attends k-block j iff map[h,i,j] != 0.
+ * Stands behind dynamic_block_sparse_fwd_flashinfer's wrapper.plan (svg/kmeans_utils.py:1355-1385).
+ *   map    uint8 [BH, QC, KC]     row_sz int32 [BH, QC]     col_sz int32 [BH, KC]
+ * Each head's row sizes and col sizes must sum to S (not checked on device). */
+int svgb_attn_plan_varblock_bytes(int BH, int S, int QC, int KC, size_t* bytes);
+int svgb_attn_plan_varblock(const uint8_t* map, const int32_t* row_sz, const int32_t* col_sz, int BH,
+                            int S, int QC, int KC, void* plan_ws, size_t ws_bytes, svgb_plan* plan,
+                            void* stream);
+
+/* SVG1: one element-exact band mask shared by every head.  Stands behind prepare_flexattention /
+ * create_block_mask (svg/models/hyvideo/attention.py:527-551). */
+int svgb_attn_plan_band_bytes(int S, size_t* bytes);
+int svgb_attn_plan_band(int mask_mode, int m0, int m1, int m2, int BH, int S, void* plan_ws,
+                        size_t ws_bytes, svgb_plan* plan, void* stream);
+
+/* ---- attention -------------------------------------------------------------------------- */
+/* o = softmax(q k^T * sm_scale  [masked by plan]) v, per head.  Stands behind
+ * dynamic_block_sparse_fwd_flashinfer (svg/kmeans_utils.py:1319-1392), flex_attention under the
+ * SVG1 BlockMask (hyvideo/attention.py:401-403), the BSR ops (svg/kernels/ops/attention_ops.py:
+ * 140-197) and the dense fall-backs.
+ *   q,k,v : [BH, S, D] with explicit strides (elements): element (h,s,d) at h*head_stride +
+ *           s*row_stride + d.  [B,H,S,D] contiguous: row_stride=D, head_stride=S*D.
+ *           [S,H,D]: row_stride=H*D, head_stride=D.   D in {64,128}; base pointers 16-B aligned,
+ *           strides multiples of 8 elements.
+ *   o     : same addressing with its own strides.
+ *   o_rows: optional int32 [BH,S]; when non-NULL output row for query row s is o_rows[h,s]
+ *           (fuses apply_inverse_permutation_triton, svg/kernels/triton/permute.py:131-170).
+ *   lse   : optional float [BH,S], natural-log log-sum-exp of the scaled scores.
+ *   plan  : host pointer. */
+int svgb_attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse,
+                  const int32_t* o_rows, int dtype, int BH, int S, int D, long long row_stride,
+                  long long head_stride, long long o_row_stride, long long o_head_stride,
+                  float sm_scale, const svgb_plan* plan, const void* plan_ws, void* stream);
+
+/* density of a variable-block map (density_calculation, svg/kmeans_utils.py:13-31) -> float [BH] */
+int svgb_density(const uint8_t* map, const int32_t* row_sz, const int32_t* col_sz, int BH, int QC,
+                 int KC, float* density, void* stream);
+
+/* ---- layout transforms ------------------------------------------------------------------ */
+/* stable ascending argsort of labels in [0,K): perm int32 [BH,S] (sorted_indices of
+ * permute_tensor_by_labels_triton, permute.py:113) and counts int32 [BH,K] (cluster sizes). */
+int svgb_argsort_labels_bytes(int BH, int S, int K, size_t* bytes);
+int svgb_argsort_labels(const int32_t* labels, int BH, int S, int K, int32_t* perm, int32_t* counts,
+                        void* ws, size_t ws_bytes, void* stream);
+/* out[h,s,:] = in[h,perm[h,s],:]   (_permute_kernel, permute.py:12-43);  16-bit elements */
+int svgb_permute_gather(const void* in, const int32_t* perm, void* out, int BH, int S, int D,
+                        void* stream);
+/* out[h,perm[h,s],:] = in[h,s,:]   (_inverse_permute_kernel, permute.py:46-75) */
+int svgb_permute_scatter(const void* in, const int32_t* perm, void* out, int BH, int S, int D,
+                         void* stream);
+/* SVG1 head placement (hunyuan_sparse_head_placement, hyvideo/placement.py:34-153): for heads with
+ * best_mask_idx==1 the video part goes frame-major -> token-major (dst = patch*F + frame), text
+ * untouched; other heads are copied.  text_first=1 selects the CogVideoX variant
+ * (cog/placement.py).  inverse=1 is hunyuan_hidden_states_placement (placement.py:285-387).
+ * n_tensors in {1,2,3}: in/out arrays of that many [BH,S,D] 16-bit tensors. */
+int svgb_head_placement(const void* const* in, void* const* out, int n_tensors,
+                        const int32_t* best_mask_idx, int BH, int S, int D, int ctx, int F, int P,
+                        int text_first, int inverse, void* stream);
+
+/* ---- flash k-means (svg/kmeans_utils.py:464-733) ------------------------------------------ */
+/* nearest centroid per point: argmin_k max(0, |x|^2 + |c_k|^2 - 2 x.c_k); x,c bf16 [BH,N,D],
+ * [BH,K,D]; x_sq float [BH,N]; labels int32 [BH,N].  (_euclid_assign_kernel :464-554) */
+int svgb_kmeans_assign(const void* x, const void* c, const float* x_sq, int32_t* labels, int BH,
+                       int N, int K, int D, int dtype, void* stream);
+/* centroid update (triton_centroid_update_sorted_euclid :375-421): fp32 mean of members, empty
+ * cluster keeps old centroid; deterministic (no float atomics).  Also returns counts. */
+int svgb_kmeans_update_bytes(int BH, int N, int K, int D, size_t* bytes);
+int svgb_kmeans_update(const void* x, const int32_t* labels, const void* c_old, void* c_new,
+                       int32_t* counts, float* shift_max /* [1], max_k |dc| */, int BH, int N, int K,
+                       int D, int dtype, void* ws, size_t ws_bytes, void* stream);
+/* x_sq[h,n] = sum_d x^2 computed in the input dtype's rounding (batch_kmeans_Euclid :704) */
+int svgb_row_sqnorm(const void* x, float* x_sq, int BH, int N, int D, int dtype, void* stream);
+
+/* ---- mask selection --------------------------------------------------------------------- */
+/* identify_dynamic_map (svg/kmeans_utils.py:864-896): qc [BH,QC,D], kc [BH,KC,D] 16-bit,
+ * k_sizes int32 [BH,KC] -> map uint8 [BH,QC,KC].  Ties in the descending sort resolve to the
+ * lower column index (stable). */
+int svgb_dynamic_map(const void* qc, const void* kc, const int32_t* k_sizes, int BH, int QC, int KC,
+                     int D, int dtype, float top_p, int preserve, uint8_t* map, void* stream);
+/* sample_mse (hyvideo/attention.py:375-399): MSE between full attention and attention under the two
+ * profiling masks (0 spatial, 1 temporal) on `n_rows` sampled query rows -> float [2, BH].
+ * layout: 0 = HY (text last, band 1.5*P), 1 = WAN (first-frame sink, band 2*P), 2 = COG. */
+int svgb_sample_mse_bytes(int BH, int S, int D, int n_rows, size_t* bytes);
+int svgb_sample_mse(const void* q, const void* k, const void* v, const int32_t* rows, int n_rows,
+                    int BH, int S, int D, int dtype, int layout, int ctx, int F, int P, float* mse,
+                    void* ws, size_t ws_bytes, void* stream);
+
+/* ---- self tests (debug; exercised by tests/ on the GPU) ----------------------------------- */
+/* One 128x128xD tile through the exact descriptor paths the attention kernel uses:
+ * s_out[128,128] = q k^T (fp32), o_out[128,D] = bf16(s*p_scale) v (fp32). */
+int svgb_selftest_tile(const void* q, const void* k, const void* v, float* s_out, float* o_out,
+                       int D, int dtype, float p_scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SVGB200_H_ */

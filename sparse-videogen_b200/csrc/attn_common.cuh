@@ -1,0 +1,74 @@
+// Shared definitions for the block-sparse attention path: the device-resident "plan" (work items +
+// KV chunk lists) that every mask family (SVG2 variable blocks, SVG1 band masks, BSR, dense) is
+// lowered to, and the element-mask predicates used on partial tiles.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace svgb {
+
+// One work item = one CTA: up to 256 consecutive query rows of one head (two 128-row MMA tiles that
+// share every K/V tile) and a list of KV chunks.
+//   item  = {q_row0, nrows (1..256), chunk_off, nchunks}
+//   chunk = {kv_start, meta}; meta bits [0,8) = valid columns - 1 (0..127), bit 8 = ELEM (evaluate
+//           the element mask predicate on this chunk), bit 9 = reserved.
+constexpr int kItemRows = 256;
+constexpr int kTileRows = 128;
+constexpr int kChunkCols = 128;
+constexpr int kChunkElem = 1 << 8;
+
+__host__ __device__ inline int chunk_meta(int valid, bool elem) {
+  return ((valid - 1) & 0xff) | (elem ? kChunkElem : 0);
+}
+__host__ __device__ inline int chunk_valid(int meta) { return (meta & 0xff) + 1; }
+
+// Element mask families: parameters m0,m1,m2.
+enum MaskMode : int {
+  MASK_NONE = 0,
+  // HunyuanVideo (text last), reference svg/models/hyvideo/utils.py:20-44
+  //   m0 = V = F*P, m1 = R = V + prompt_len, m2 = W
+  MASK_HY = 1,
+  // Wan / Cosmos (no text, first-frame sink), reference svg/models/wan/utils.py:25-41
+  //   m0 = P (tokens per frame), m2 = W   : kv < P | |q-kv| <= W
+  MASK_WAN = 2,
+  // CogVideoX (text first), reference svg/models/cog/utils.py:30-46
+  //   m0 = first-column limit (prompt_len or prompt_len + P), m1 = prompt_len, m2 = W
+  MASK_COG = 3,
+};
+
+__host__ __device__ inline bool mask_allowed(int mode, int q, int kv, int m0, int m1, int m2) {
+  int d = q - kv;
+  d = d < 0 ? -d : d;
+  switch (mode) {
+    case MASK_HY: {
+      bool real = (q < m1) && (kv < m1);
+      bool fake = (q >= m1) && (kv >= m1);
+      bool vid = (d < m2) || (kv >= m0) || (q >= m0);
+      return (real && vid) || fake;
+    }
+    case MASK_WAN:
+      return (kv < m0) || (d <= m2);
+    case MASK_COG:
+      return (kv < m0) || (q < m1) || (d < m2);
+    default:
+      return true;
+  }
+}
+
+struct AttnArgs {
+  const int4* items;
+  const int* item_count;
+  const int2* chunks;
+  int items_stride;   // 0: one plan shared by all heads (band masks); else items per head
+  int counts_stride;  // 0 or 1
+  void* o;
+  long long o_row_stride;   // elements
+  long long o_head_stride;  // elements
+  const int* o_rows;        // optional [BH, S]: output row for query row q (fused inverse permutation)
+  float* lse;               // optional [BH, S] (natural log), indexed like o rows
+  float scale_log2;         // softmax scale * log2(e)
+  int S;
+  int mask_mode, m0, m1, m2;
+};
+
+}  // namespace svgb

@@ -1,0 +1,433 @@
+// Attention plans (device-built work lists), the attention launcher, density, and the tile
+// self-test.  See attn_kernel.cuh for the kernel itself.
+#include "../../include/svgb200.h"
+#include "attn_kernel.cuh"
+#include "host_common.h"
+
+namespace svgb {
+
+// =============================================================================================
+// Plan: variable blocks (SVG2 dynamic map / BSR / dense)
+//   one CTA per head; thread per q-block walks its map row, merges selected k-blocks that are
+//   adjacent in token space into runs and cuts runs into <=128-column chunks.
+// =============================================================================================
+__global__ void plan_varblock_kernel(const uint8_t* __restrict__ map, const int* __restrict__ row_sz,
+                                     const int* __restrict__ col_sz, int QC, int KC, int max_items,
+                                     int chunk_cap, int* __restrict__ counts, int4* __restrict__ items,
+                                     int2* __restrict__ chunks) {
+  extern __shared__ int sm[];
+  int* coloff = sm;                 // KC + 1
+  int* rowoff = coloff + KC + 1;    // QC + 1
+  int* itembase = rowoff + QC + 1;  // QC + 1
+  const int bh = blockIdx.x;
+  row_sz += static_cast<size_t>(bh) * QC;
+  col_sz += static_cast<size_t>(bh) * KC;
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int j = 0; j < KC; ++j) {
+      coloff[j] = acc;
+      acc += col_sz[j];
+    }
+    coloff[KC] = acc;
+  }
+  if (threadIdx.x == 32) {
+    int acc = 0, it = 0;
+    for (int i = 0; i < QC; ++i) {
+      rowoff[i] = acc;
+      itembase[i] = it;
+      const int r = row_sz[i];
+      acc += r;
+      it += (r + kItemRows - 1) / kItemRows;
+    }
+    rowoff[QC] = acc;
+    itembase[QC] = it;
+    counts[bh] = it < max_items ? it : max_items;
+  }
+  __syncthreads();
+  for (int qb = threadIdx.x; qb < QC; qb += blockDim.x) {
+    const int r = rowoff[qb + 1] - rowoff[qb];
+    if (r == 0) continue;
+    const size_t list = (static_cast<size_t>(bh) * QC + qb) * chunk_cap;
+    int2* out = chunks + list;
+    const uint8_t* mrow = map + (static_cast<size_t>(bh) * QC + qb) * KC;
+    int n = 0;
+    int run_s = -1, run_e = -1;
+    for (int j = 0; j <= KC; ++j) {
+      bool sel = false;
+      int s = 0, e = 0;
+      if (j < KC) {
+        s = coloff[j];
+        e = coloff[j + 1];
+        sel = (mrow[j] != 0) && (e > s);
+      }
+      if (sel && run_s >= 0 && s == run_e) {
+        run_e = e;  // contiguous in token space: extend
+        continue;
+      }
+      if (run_s >= 0 && (sel || j == KC)) {
+        for (int p = run_s; p < run_e && n < chunk_cap; p += kChunkCols) {
+          const int valid = min(kChunkCols, run_e - p);
+          out[n++] = make_int2(p, chunk_meta(valid, false));
+        }
+        run_s = -1;
+      }
+      if (sel) {
+        run_s = s;
+        run_e = e;
+      }
+    }
+    const int nit = (r + kItemRows - 1) / kItemRows;
+    for (int t = 0; t < nit; ++t) {
+      const int idx = itembase[qb] + t;
+      if (idx < max_items)
+        items[static_cast<size_t>(bh) * max_items + idx] =
+            make_int4(rowoff[qb] + t * kItemRows, min(kItemRows, r - t * kItemRows),
+                      static_cast<int>(list), n);
+    }
+  }
+}
+
+// =============================================================================================
+// Plan: element-exact band masks (SVG1).  One CTA per 256-row item; thread = query row; for every
+// 128-column chunk the block votes any/all over the item's rows.  Exact by construction.
+// =============================================================================================
+__global__ void plan_band_kernel(int mode, int m0, int m1, int m2, int S, int n_chunks_total,
+                                 int* __restrict__ counts, int4* __restrict__ items,
+                                 int2* __restrict__ chunks) {
+  const int item = blockIdx.x;
+  const int q = item * kItemRows + threadIdx.x;
+  const bool row_live = q < S;
+  int2* out = chunks + static_cast<size_t>(item) * n_chunks_total;
+  int n = 0;
+  for (int c = 0; c < n_chunks_total; ++c) {
+    const int kv0 = c * kChunkCols;
+    const int valid = min(kChunkCols, S - kv0);
+    bool any = false, all = true;
+    if (row_live) {
+      for (int i = 0; i < valid; ++i) {
+        const bool a = mask_allowed(mode, q, kv0 + i, m0, m1, m2);
+        any |= a;
+        all &= a;
+      }
+    }
+    const int block_any = __syncthreads_or(any ? 1 : 0);
+    const int block_all = __syncthreads_and((all || !row_live) ? 1 : 0);
+    if (block_any) {
+      if (threadIdx.x == 0) out[n] = make_int2(kv0, chunk_meta(valid, !block_all));
+      ++n;
+    }
+  }
+  if (threadIdx.x == 0) {
+    items[item] = make_int4(item * kItemRows, min(kItemRows, S - item * kItemRows),
+                            static_cast<int>(static_cast<size_t>(item) * n_chunks_total), n);
+    if (item == 0) counts[0] = gridDim.x;
+  }
+}
+
+// =============================================================================================
+// density_calculation (svg/kmeans_utils.py:13-31)
+// =============================================================================================
+__global__ void density_kernel(const uint8_t* __restrict__ map, const int* __restrict__ row_sz,
+                               const int* __restrict__ col_sz, int QC, int KC,
+                               float* __restrict__ density) {
+  const int bh = blockIdx.x;
+  __shared__ unsigned long long s_num[32], s_den[32];
+  unsigned long long num = 0, den = 0;
+  for (int idx = threadIdx.x; idx < QC * KC; idx += blockDim.x) {
+    const int i = idx / KC, j = idx - i * KC;
+    const unsigned long long a =
+        static_cast<unsigned long long>(row_sz[static_cast<size_t>(bh) * QC + i]) *
+        static_cast<unsigned long long>(col_sz[static_cast<size_t>(bh) * KC + j]);
+    den += a;
+    if (map[(static_cast<size_t>(bh) * QC + i) * KC + j]) num += a;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    num += __shfl_xor_sync(0xffffffffu, num, o);
+    den += __shfl_xor_sync(0xffffffffu, den, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    s_num[threadIdx.x >> 5] = num;
+    s_den[threadIdx.x >> 5] = den;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    num = den = 0;
+    for (int w = 0; w < (blockDim.x + 31) / 32; ++w) {
+      num += s_num[w];
+      den += s_den[w];
+    }
+    density[bh] = static_cast<float>(static_cast<double>(num) / static_cast<double>(den));
+  }
+}
+
+// =============================================================================================
+// Tile self-test: the exact descriptor paths of the attention kernel on one 128x128xD tile.
+// =============================================================================================
+template <int D, bool BF16>
+__global__ void __launch_bounds__(128, 1)
+selftest_tile_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant__ CUtensorMap kmap,
+                     const __grid_constant__ CUtensorMap vmap, float* __restrict__ s_out,
+                     float* __restrict__ o_out, float p_scale) {
+  using Cfg = AttnCfg<D>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t sQ = smem_base, sK = sQ + Cfg::kTileBytes, sV = sK + Cfg::kTileBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_al + 3 * Cfg::kTileBytes);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t ld_bar = smem_u32(&bars[0]), mma_bar = smem_u32(&bars[1]), mma2_bar = smem_u32(&bars[2]);
+  if (threadIdx.x == 0) {
+    mbar_init(ld_bar, 1);
+    mbar_init(mma_bar, 1);
+    mbar_init(mma2_bar, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc<256>(smem_u32(tmem_slot));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(ld_bar, 3 * Cfg::kTileBytes);
+    for (int h = 0; h < Cfg::kHalves; ++h) {
+      tma_load_3d(sQ + h * Cfg::kPanelBytes, &qmap, ld_bar, h * 64, 0, 0);
+      tma_load_3d(sK + h * Cfg::kPanelBytes, &kmap, ld_bar, h * 64, 0, 0);
+      tma_load_3d(sV + h * Cfg::kPanelBytes, &vmap, ld_bar, h * 64, 0, 0);
+    }
+    mbar_wait(ld_bar, 0, 20);
+    const uint32_t idesc = make_idesc(128, 128, BF16, false, false);
+#pragma unroll
+    for (int kk = 0; kk < D / 16; ++kk) {
+      const uint32_t off = (kk >> 2) * Cfg::kPanelBytes + (kk & 3) * 32;
+      mma_ss(tmem + 0, desc_kmajor_sw128(sQ + off), desc_kmajor_sw128(sK + off), idesc, kk > 0);
+    }
+    tc_commit(mma_bar);
+  }
+  // S -> global, P = 16-bit(S * p_scale) -> TMEM columns [0,64)
+  mbar_wait(mma_bar, 0, 21);
+  tc_fence_after();
+  const int row = warp * 32 + lane;
+  const uint32_t lane_addr = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+  for (int g = 0; g < 4; ++g) {
+    uint32_t r[32];
+    tmem_ld32(lane_addr + g * 32, r);
+    tc_wait_ld();
+    uint32_t pk[16];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) s_out[row * 128 + g * 32 + i] = __uint_as_float(r[i]);
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      pk[i] = pack2<BF16>(__uint_as_float(r[2 * i]) * p_scale, __uint_as_float(r[2 * i + 1]) * p_scale);
+    tmem_st16(lane_addr + g * 16, pk);
+  }
+  tc_wait_st();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (threadIdx.x == 0) {
+    const uint32_t idesc = make_idesc(128, D, BF16, false, true);
+    for (int kk = 0; kk < 8; ++kk)
+      mma_ts(tmem + 128, tmem + kk * 8, desc_mnmajor_sw128(sV + kk * 2048, Cfg::kPanelBytes), idesc,
+             kk > 0);
+    tc_commit(mma2_bar);
+  }
+  mbar_wait(mma2_bar, 0, 22);
+  tc_fence_after();
+  for (int g = 0; g < D / 32; ++g) {
+    uint32_t r[32];
+    tmem_ld32(lane_addr + 128 + g * 32, r);
+    tc_wait_ld();
+#pragma unroll
+    for (int i = 0; i < 32; ++i) o_out[row * D + g * 32 + i] = __uint_as_float(r[i]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<256>(tmem);
+  }
+}
+
+template <int D, bool BF16>
+static int launch_attn(const CUtensorMap& qm, const CUtensorMap& km, const CUtensorMap& vm,
+                       const AttnArgs& args, dim3 grid, cudaStream_t stream) {
+  using Cfg = AttnCfg<D>;
+  auto kern = attn_fwd_kernel<D, BF16>;
+  SVGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+  kern<<<grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(qm, km, vm, args);
+  SVGB_LAUNCH_OK();
+  return 0;
+}
+
+template <int D, bool BF16>
+static int launch_selftest(const CUtensorMap& qm, const CUtensorMap& km, const CUtensorMap& vm,
+                           float* s_out, float* o_out, float p_scale, cudaStream_t stream) {
+  using Cfg = AttnCfg<D>;
+  auto kern = selftest_tile_kernel<D, BF16>;
+  const int smem = 1024 + 3 * Cfg::kTileBytes + 256;
+  SVGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  kern<<<1, 128, smem, stream>>>(qm, km, vm, s_out, o_out, p_scale);
+  SVGB_LAUNCH_OK();
+  return 0;
+}
+
+static int varblock_chunk_cap(int S, int KC) { return S / kChunkCols + (KC + 1) / 2 + 2; }
+static int varblock_max_items(int S, int QC) { return S / kItemRows + QC + 1; }
+
+}  // namespace svgb
+
+using namespace svgb;
+
+extern "C" {
+
+int svgb_attn_plan_varblock_bytes(int BH, int S, int QC, int KC, size_t* bytes) {
+  SVGB_REQUIRE(BH > 0 && S > 0 && QC > 0 && KC > 0 && bytes, "bad arguments");
+  const size_t counts = align_up(sizeof(int) * BH, 256);
+  const size_t items = align_up(sizeof(int4) * BH * varblock_max_items(S, QC), 256);
+  const size_t chunks = align_up(sizeof(int2) * static_cast<size_t>(BH) * QC * varblock_chunk_cap(S, KC), 256);
+  *bytes = counts + items + chunks;
+  return 0;
+}
+
+int svgb_attn_plan_varblock(const uint8_t* map, const int32_t* row_sz, const int32_t* col_sz, int BH,
+                            int S, int QC, int KC, void* plan_ws, size_t ws_bytes, svgb_plan* plan,
+                            void* stream) {
+  size_t need = 0;
+  if (svgb_attn_plan_varblock_bytes(BH, S, QC, KC, &need)) return -1;
+  SVGB_REQUIRE(map && row_sz && col_sz && plan_ws && plan, "null pointer");
+  SVGB_REQUIRE(ws_bytes >= need, "plan workspace too small: %zu < %zu", ws_bytes, need);
+  SVGB_REQUIRE(static_cast<size_t>(BH) * QC * varblock_chunk_cap(S, KC) < (1ull << 31),
+               "plan too large for 32-bit chunk offsets");
+  const int max_items = varblock_max_items(S, QC);
+  const int cap = varblock_chunk_cap(S, KC);
+  plan->kind = 1;
+  plan->BH = BH;
+  plan->S = S;
+  plan->max_items = max_items;
+  plan->items_stride = max_items;
+  plan->counts_stride = 1;
+  plan->mask_mode = MASK_NONE;
+  plan->m0 = plan->m1 = plan->m2 = 0;
+  plan->counts_off = 0;
+  plan->items_off = align_up(sizeof(int) * BH, 256);
+  plan->chunks_off = plan->items_off + align_up(sizeof(int4) * BH * max_items, 256);
+  plan->bytes = need;
+  char* ws = static_cast<char*>(plan_ws);
+  const size_t smem = sizeof(int) * (KC + 1 + 2 * (QC + 1));
+  SVGB_REQUIRE(smem <= 48 * 1024, "QC/KC too large for the plan kernel (%zu B smem)", smem);
+  plan_varblock_kernel<<<BH, 256, smem, static_cast<cudaStream_t>(stream)>>>(
+      map, row_sz, col_sz, QC, KC, max_items, cap, reinterpret_cast<int*>(ws + plan->counts_off),
+      reinterpret_cast<int4*>(ws + plan->items_off), reinterpret_cast<int2*>(ws + plan->chunks_off));
+  SVGB_LAUNCH_OK();
+  return 0;
+}
+
+int svgb_attn_plan_band_bytes(int S, size_t* bytes) {
+  SVGB_REQUIRE(S > 0 && bytes, "bad arguments");
+  const size_t n_items = (S + kItemRows - 1) / kItemRows;
+  const size_t n_chunks = (S + kChunkCols - 1) / kChunkCols;
+  *bytes = 256 + align_up(sizeof(int4) * n_items, 256) + align_up(sizeof(int2) * n_items * n_chunks, 256);
+  return 0;
+}
+
+int svgb_attn_plan_band(int mask_mode, int m0, int m1, int m2, int BH, int S, void* plan_ws,
+                        size_t ws_bytes, svgb_plan* plan, void* stream) {
+  size_t need = 0;
+  if (svgb_attn_plan_band_bytes(S, &need)) return -1;
+  SVGB_REQUIRE(plan_ws && plan, "null pointer");
+  SVGB_REQUIRE(ws_bytes >= need, "plan workspace too small: %zu < %zu", ws_bytes, need);
+  SVGB_REQUIRE(mask_mode >= MASK_NONE && mask_mode <= MASK_COG, "unknown mask mode %d", mask_mode);
+  const int n_items = (S + kItemRows - 1) / kItemRows;
+  const int n_chunks = (S + kChunkCols - 1) / kChunkCols;
+  SVGB_REQUIRE(static_cast<size_t>(n_items) * n_chunks < (1ull << 31), "plan too large");
+  plan->kind = 2;
+  plan->BH = BH;
+  plan->S = S;
+  plan->max_items = n_items;
+  plan->items_stride = 0;
+  plan->counts_stride = 0;
+  plan->mask_mode = mask_mode;
+  plan->m0 = m0;
+  plan->m1 = m1;
+  plan->m2 = m2;
+  plan->counts_off = 0;
+  plan->items_off = 256;
+  plan->chunks_off = 256 + align_up(sizeof(int4) * n_items, 256);
+  plan->bytes = need;
+  char* ws = static_cast<char*>(plan_ws);
+  plan_band_kernel<<<n_items, kItemRows, 0, static_cast<cudaStream_t>(stream)>>>(
+      mask_mode, m0, m1, m2, S, n_chunks, reinterpret_cast<int*>(ws + plan->counts_off),
+      reinterpret_cast<int4*>(ws + plan->items_off), reinterpret_cast<int2*>(ws + plan->chunks_off));
+  SVGB_LAUNCH_OK();
+  return 0;
+}
+
+int svgb_attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse,
+                  const int32_t* o_rows, int dtype, int BH, int S, int D, long long row_stride,
+                  long long head_stride, long long o_row_stride, long long o_head_stride,
+                  float sm_scale, const svgb_plan* plan, const void* plan_ws, void* stream) {
+  SVGB_REQUIRE(q && k && v && o && plan && plan_ws, "null pointer");
+  SVGB_REQUIRE(D == 64 || D == 128, "head_dim %d unsupported (64 or 128)", D);
+  SVGB_REQUIRE(dtype == SVGB_BF16 || dtype == SVGB_F16, "dtype %d unsupported", dtype);
+  SVGB_REQUIRE(plan->S == S && (plan->items_stride == 0 || plan->BH == BH),
+               "plan was built for BH=%d S=%d, called with BH=%d S=%d", plan->BH, plan->S, BH, S);
+  SVGB_REQUIRE((reinterpret_cast<uintptr_t>(o) & 15) == 0 && o_row_stride % 8 == 0 && o_head_stride % 8 == 0,
+               "output must be 16-byte aligned with strides multiple of 8 elements");
+  CUtensorMap qm, km, vm;
+  if (encode_tmap_hsd(&qm, q, dtype, BH, S, D, row_stride, head_stride)) return -1;
+  if (encode_tmap_hsd(&km, k, dtype, BH, S, D, row_stride, head_stride)) return -1;
+  if (encode_tmap_hsd(&vm, v, dtype, BH, S, D, row_stride, head_stride)) return -1;
+  const char* ws = static_cast<const char*>(plan_ws);
+  AttnArgs a;
+  a.items = reinterpret_cast<const int4*>(ws + plan->items_off);
+  a.item_count = reinterpret_cast<const int*>(ws + plan->counts_off);
+  a.chunks = reinterpret_cast<const int2*>(ws + plan->chunks_off);
+  a.items_stride = plan->items_stride;
+  a.counts_stride = plan->counts_stride;
+  a.o = o;
+  a.o_row_stride = o_row_stride;
+  a.o_head_stride = o_head_stride;
+  a.o_rows = o_rows;
+  a.lse = lse;
+  a.scale_log2 = sm_scale * 1.4426950408889634f;
+  a.S = S;
+  a.mask_mode = plan->mask_mode;
+  a.m0 = plan->m0;
+  a.m1 = plan->m1;
+  a.m2 = plan->m2;
+  dim3 grid(plan->max_items, BH);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (D == 128) {
+    return dtype == SVGB_BF16 ? launch_attn<128, true>(qm, km, vm, a, grid, st)
+                              : launch_attn<128, false>(qm, km, vm, a, grid, st);
+  }
+  return dtype == SVGB_BF16 ? launch_attn<64, true>(qm, km, vm, a, grid, st)
+                            : launch_attn<64, false>(qm, km, vm, a, grid, st);
+}
+
+int svgb_density(const uint8_t* map, const int32_t* row_sz, const int32_t* col_sz, int BH, int QC,
+                 int KC, float* density, void* stream) {
+  SVGB_REQUIRE(map && row_sz && col_sz && density && BH > 0 && QC > 0 && KC > 0, "bad arguments");
+  density_kernel<<<BH, 256, 0, static_cast<cudaStream_t>(stream)>>>(map, row_sz, col_sz, QC, KC, density);
+  SVGB_LAUNCH_OK();
+  return 0;
+}
+
+int svgb_selftest_tile(const void* q, const void* k, const void* v, float* s_out, float* o_out,
+                       int D, int dtype, float p_scale, void* stream) {
+  SVGB_REQUIRE(q && k && v && s_out && o_out, "null pointer");
+  SVGB_REQUIRE(D == 64 || D == 128, "head_dim %d unsupported", D);
+  CUtensorMap qm, km, vm;
+  if (encode_tmap_hsd(&qm, q, dtype, 1, 128, D, D, 128LL * D)) return -1;
+  if (encode_tmap_hsd(&km, k, dtype, 1, 128, D, D, 128LL * D)) return -1;
+  if (encode_tmap_hsd(&vm, v, dtype, 1, 128, D, D, 128LL * D)) return -1;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (D == 128)
+    return dtype == SVGB_BF16 ? launch_selftest<128, true>(qm, km, vm, s_out, o_out, p_scale, st)
+                              : launch_selftest<128, false>(qm, km, vm, s_out, o_out, p_scale, st);
+  return dtype == SVGB_BF16 ? launch_selftest<64, true>(qm, km, vm, s_out, o_out, p_scale, st)
+                            : launch_selftest<64, false>(qm, km, vm, s_out, o_out, p_scale, st);
+}
+
+}  // extern "C"

@@ -1,0 +1,354 @@
+// Block-sparse flash attention forward for sm_100a.
+//
+// One CTA per work item (<= 256 query rows of one head = two 128-row tiles T0,T1 that share every
+// K/V tile).  Warp roles (12 warps, 1 CTA / SM):
+//   warp 0      TMA producer : Q once, then K(0) V(0) K(1) V(1) ... through one smem ring
+//   warp 1      MMA issuer   : S_t = Q_t K^T (SS, K-major, tcgen05) ; O_t += P_t V (TS: P from TMEM,
+//                              V MN-major from smem).  Issue order  PV0(j) QK0(j+1) PV1(j) QK1(j+1)
+//                              so the softmax of one tile overlaps the MMAs of the other.
+//   warp 2      TMEM allocator (512 columns: S0 | S1 | O0 | O1), otherwise idle
+//   warps 4-7   softmax + correction + epilogue for T0 (one thread per query row)
+//   warps 8-11  same for T1
+// P (bf16/fp16) overwrites the first half of its S tile in TMEM; O is rescaled lazily (only when the
+// running max grows by more than 2^8) by the row's own softmax thread, which is safe because the
+// S_t(j) commit also covers PV_t(j-1).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include "attn_common.cuh"
+#include "ptx.cuh"
+
+namespace svgb {
+
+template <int D>
+struct AttnCfg {
+  static_assert(D == 64 || D == 128, "head_dim must be 64 or 128");
+  static constexpr int kHalves = D / 64;                 // 64-column (128-byte) swizzle panels
+  static constexpr int kPanelBytes = 128 * 128;          // 128 rows x 128 B
+  static constexpr int kTileBytes = kPanelBytes * kHalves;
+  static constexpr int kStages = (D == 128) ? 5 : 8;
+  static constexpr int kQBytes = 2 * kTileBytes;
+  static constexpr int kRingBytes = kStages * kTileBytes;
+  static constexpr int kBarBytes = 1024;
+  static constexpr int kSmemBytes = 1024 /*align slack*/ + kQBytes + kRingBytes + kBarBytes;
+  static constexpr int kThreads = 384;
+  static constexpr uint32_t kTmemCols = 512;
+  static constexpr int kSCol0 = 0, kSCol1 = 128, kOCol0 = 256, kOCol1 = 256 + D;
+};
+
+struct AttnBars {
+  uint64_t q_full;
+  uint64_t o_final;
+  uint64_t s_full[2];
+  uint64_t p_full[2];
+  uint64_t kv_full[8];
+  uint64_t kv_empty[8];
+  uint32_t tmem_base;
+};
+
+constexpr float kRescaleTau = 8.0f;  // log2 units
+
+template <int D, bool BF16>
+__global__ void __launch_bounds__(384, 1)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant__ CUtensorMap kmap,
+                const __grid_constant__ CUtensorMap vmap, const AttnArgs args) {
+  using Cfg = AttnCfg<D>;
+  const int bh = blockIdx.y;
+  const int n_items = args.item_count[bh * args.counts_stride];
+  if (static_cast<int>(blockIdx.x) >= n_items) return;
+  const int4 item = args.items[static_cast<size_t>(bh) * args.items_stride + blockIdx.x];
+  const int q_row0 = item.x, nrows = item.y, chunk0 = item.z, nchunks = item.w;
+  const int ntiles = nrows > kTileRows ? 2 : 1;
+  const int2* __restrict__ chunks = args.chunks + chunk0;
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t sQ = smem_base;
+  const uint32_t sRing = smem_base + Cfg::kQBytes;
+  AttnBars* bars = reinterpret_cast<AttnBars*>(smem_al + Cfg::kQBytes + Cfg::kRingBytes);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&qmap);
+    tma_prefetch_desc(&kmap);
+    tma_prefetch_desc(&vmap);
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(smem_u32(&bars->q_full), 1);
+    mbar_init(smem_u32(&bars->o_final), 1);
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(smem_u32(&bars->s_full[t]), 1);
+      mbar_init(smem_u32(&bars->p_full[t]), 128);
+    }
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      mbar_init(smem_u32(&bars->kv_full[s]), 1);
+      mbar_init(smem_u32(&bars->kv_empty[s]), 1);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 2) tmem_alloc<Cfg::kTmemCols>(smem_u32(&bars->tmem_base));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = bars->tmem_base;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      const uint32_t qbar = smem_u32(&bars->q_full);
+      mbar_expect_tx(qbar, ntiles * Cfg::kTileBytes);
+      for (int t = 0; t < ntiles; ++t)
+        for (int h = 0; h < Cfg::kHalves; ++h)
+          tma_load_3d(sQ + t * Cfg::kTileBytes + h * Cfg::kPanelBytes, &qmap, qbar, h * 64,
+                      q_row0 + t * kTileRows, bh);
+      int it = 0;
+      for (int j = 0; j < nchunks; ++j) {
+        const int kv0 = __ldg(&chunks[j].x);
+#pragma unroll
+        for (int kv = 0; kv < 2; ++kv, ++it) {
+          const int slot = it % Cfg::kStages;
+          const uint32_t ph = (it / Cfg::kStages) & 1;
+          mbar_wait(smem_u32(&bars->kv_empty[slot]), ph ^ 1, 1);
+          const uint32_t fb = smem_u32(&bars->kv_full[slot]);
+          mbar_expect_tx(fb, Cfg::kTileBytes);
+          const CUtensorMap* map = kv == 0 ? &kmap : &vmap;
+          for (int h = 0; h < Cfg::kHalves; ++h)
+            tma_load_3d(sRing + slot * Cfg::kTileBytes + h * Cfg::kPanelBytes, map, fb, h * 64, kv0,
+                        bh);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0 && nchunks > 0) {
+      auto issue_qk = [&](int t, int slot, int ncols) {
+        const uint32_t idesc = make_idesc(128, ncols, BF16, false, false);
+        const uint32_t d_tmem = tmem + (t == 0 ? Cfg::kSCol0 : Cfg::kSCol1);
+#pragma unroll
+        for (int kk = 0; kk < D / 16; ++kk) {
+          const uint32_t off = (kk >> 2) * Cfg::kPanelBytes + (kk & 3) * 32;
+          const uint64_t a = desc_kmajor_sw128(sQ + t * Cfg::kTileBytes + off);
+          const uint64_t b = desc_kmajor_sw128(sRing + slot * Cfg::kTileBytes + off);
+          mma_ss(d_tmem, a, b, idesc, kk > 0 ? 1u : 0u);
+        }
+      };
+      auto issue_pv = [&](int t, int slot, int ncols, bool acc) {
+        const uint32_t idesc = make_idesc(128, D, BF16, false, true);
+        const uint32_t d_tmem = tmem + (t == 0 ? Cfg::kOCol0 : Cfg::kOCol1);
+        const uint32_t p_tmem = tmem + (t == 0 ? Cfg::kSCol0 : Cfg::kSCol1);
+        const int nk = ncols >> 4;
+        for (int kk = 0; kk < nk; ++kk) {
+          // 16 kv rows per MMA: 16 x 128 B = 2048 B down the V panel; P advances 8 TMEM columns.
+          const uint64_t b =
+              desc_mnmajor_sw128(sRing + slot * Cfg::kTileBytes + kk * 2048, Cfg::kPanelBytes);
+          mma_ts(d_tmem, p_tmem + kk * 8, b, idesc, (acc || kk > 0) ? 1u : 0u);
+        }
+      };
+      auto round16 = [](int meta) { return (chunk_valid(meta) + 15) & ~15; };
+
+      mbar_wait(smem_u32(&bars->q_full), 0, 2);
+      int ring = 0;
+      int n_cur = round16(__ldg(&chunks[0].y));
+      {
+        const int slot = 0;
+        mbar_wait(smem_u32(&bars->kv_full[slot]), 0, 3);
+        tc_fence_after();
+        issue_qk(0, slot, n_cur);
+        tc_commit(smem_u32(&bars->s_full[0]));
+        if (ntiles > 1) {
+          issue_qk(1, slot, n_cur);
+          tc_commit(smem_u32(&bars->s_full[1]));
+        }
+        tc_commit(smem_u32(&bars->kv_empty[slot]));
+        ring = 1;
+      }
+      for (int j = 0; j < nchunks; ++j) {
+        const bool has_next = (j + 1 < nchunks);
+        const int vslot = ring % Cfg::kStages;
+        const uint32_t vph = (ring / Cfg::kStages) & 1;
+        ++ring;
+        int kslot = 0, n_next = 0;
+        uint32_t kph = 0;
+        if (has_next) {
+          kslot = ring % Cfg::kStages;
+          kph = (ring / Cfg::kStages) & 1;
+          ++ring;
+          n_next = round16(__ldg(&chunks[j + 1].y));
+        }
+        mbar_wait(smem_u32(&bars->kv_full[vslot]), vph, 4);
+        mbar_wait(smem_u32(&bars->p_full[0]), j & 1, 5);
+        tc_fence_after();
+        issue_pv(0, vslot, n_cur, j > 0);
+        if (has_next) {
+          mbar_wait(smem_u32(&bars->kv_full[kslot]), kph, 6);
+          tc_fence_after();
+          issue_qk(0, kslot, n_next);
+          tc_commit(smem_u32(&bars->s_full[0]));
+        }
+        if (ntiles > 1) {
+          mbar_wait(smem_u32(&bars->p_full[1]), j & 1, 7);
+          tc_fence_after();
+          issue_pv(1, vslot, n_cur, j > 0);
+        }
+        tc_commit(smem_u32(&bars->kv_empty[vslot]));
+        if (has_next) {
+          if (ntiles > 1) {
+            issue_qk(1, kslot, n_next);
+            tc_commit(smem_u32(&bars->s_full[1]));
+          }
+          tc_commit(smem_u32(&bars->kv_empty[kslot]));
+        }
+        n_cur = n_next;
+      }
+      tc_commit(smem_u32(&bars->o_final));
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ softmax / correction / epilogue
+    const int t = (warp - 4) >> 2;
+    if (t < ntiles) {
+      const int wq = warp & 3;
+      const int row = wq * 32 + lane;  // row inside the 128-row tile == TMEM lane
+      const int q = q_row0 + t * kTileRows + row;
+      const uint32_t lane_addr = tmem + (static_cast<uint32_t>(wq * 32) << 16);
+      const uint32_t s_addr = lane_addr + (t == 0 ? Cfg::kSCol0 : Cfg::kSCol1);
+      const uint32_t o_addr = lane_addr + (t == 0 ? Cfg::kOCol0 : Cfg::kOCol1);
+      const float c = args.scale_log2;
+      const int mode = args.mask_mode, m0 = args.m0, m1 = args.m1, m2 = args.m2;
+      const uint32_t sbar = smem_u32(&bars->s_full[t]);
+      const uint32_t pbar = smem_u32(&bars->p_full[t]);
+
+      float m_used = -INFINITY;  // reference max the stored P / O are scaled against
+      float l_run = 0.f;
+      int2 ch = nchunks > 0 ? __ldg(&chunks[0]) : make_int2(0, 0);
+
+      for (int j = 0; j < nchunks; ++j) {
+        const int kv0 = ch.x;
+        const int valid = chunk_valid(ch.y);
+        const bool elem = (ch.y & kChunkElem) != 0;
+        const int ncols = (valid + 15) & ~15;
+        const int ngroups = (ncols + 31) >> 5;
+        if (j + 1 < nchunks) ch = __ldg(&chunks[j + 1]);
+
+        mbar_wait(sbar, j & 1, 8 + t);
+        tc_fence_after();
+
+        uint32_t r[32];
+        auto load_group = [&](int g) {
+          tmem_ld32(s_addr + g * 32, r);
+          tc_wait_ld();
+          if (g * 32 + 32 > valid) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (g * 32 + i >= valid) r[i] = 0xff800000u;  // -inf
+          }
+          if (elem) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (!mask_allowed(mode, q, kv0 + g * 32 + i, m0, m1, m2)) r[i] = 0xff800000u;
+          }
+        };
+
+        // pass 1: row max of the raw scores
+        float mx = -INFINITY;
+        for (int g = 0; g < ngroups; ++g) {
+          load_group(g);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
+        }
+        const float m_new = fmaxf(m_used, mx);
+        // lazy rescale: keep the stale reference max unless it grew by more than tau (log2 units)
+        float alpha = 1.f;
+        if ((m_new - m_used) * c > kRescaleTau) {  // false when both are -inf (NaN compare)
+          alpha = ex2_approx((m_used - m_new) * c);  // 0 when m_used == -inf
+          m_used = m_new;
+        }
+        if (j > 0 && __any_sync(0xffffffffu, alpha != 1.f)) {
+          // correction: O_row *= alpha (PV_t(j-1) is complete: the S_t(j) commit covered it)
+#pragma unroll 1
+          for (int g = 0; g < D / 32; ++g) {
+            uint32_t o[32];
+            tmem_ld32(o_addr + g * 32, o);
+            tc_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st32(o_addr + g * 32, o);
+          }
+        }
+        l_run *= alpha;
+        const float mc = (m_used == -INFINITY) ? 0.f : m_used * c;
+
+        // pass 2: P = exp2(S*c - m*c) -> 16-bit, packed two per TMEM column over the S tile
+        float rs = 0.f;
+        for (int g = 0; g < ngroups; ++g) {
+          load_group(g);
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float p0 = ex2_approx(fmaf(__uint_as_float(r[2 * i]), c, -mc));
+            const float p1 = ex2_approx(fmaf(__uint_as_float(r[2 * i + 1]), c, -mc));
+            rs += p0 + p1;
+            pk[i] = pack2<BF16>(p0, p1);
+          }
+          tmem_st16(s_addr + g * 16, pk);
+        }
+        l_run += rs;
+        tc_wait_st();
+        tc_fence_before();
+        mbar_arrive(pbar);
+      }
+
+      // ---------------- epilogue: O / l -> 16-bit -> global (optionally scattered rows)
+      const bool row_ok = (t * kTileRows + row) < nrows;
+      if (nchunks > 0) {
+        mbar_wait(smem_u32(&bars->o_final), 0, 10 + t);
+        tc_fence_after();
+      }
+      const float inv_l = l_run > 0.f ? 1.f / l_run : 0.f;
+      long long out_row = q;
+      if (row_ok && args.o_rows) out_row = __ldg(&args.o_rows[static_cast<size_t>(bh) * args.S + q]);
+      uint16_t* optr = reinterpret_cast<uint16_t*>(args.o) + bh * args.o_head_stride +
+                       out_row * args.o_row_stride;
+#pragma unroll 1
+      for (int g = 0; g < D / 32; ++g) {
+        uint32_t o[32];
+        if (nchunks > 0) {
+          tmem_ld32(o_addr + g * 32, o);
+          tc_wait_ld();
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[i] = 0u;
+        }
+        if (row_ok) {
+#pragma unroll
+          for (int v = 0; v < 4; ++v) {
+            uint4 w;
+            w.x = pack2<BF16>(__uint_as_float(o[8 * v + 0]) * inv_l, __uint_as_float(o[8 * v + 1]) * inv_l);
+            w.y = pack2<BF16>(__uint_as_float(o[8 * v + 2]) * inv_l, __uint_as_float(o[8 * v + 3]) * inv_l);
+            w.z = pack2<BF16>(__uint_as_float(o[8 * v + 4]) * inv_l, __uint_as_float(o[8 * v + 5]) * inv_l);
+            w.w = pack2<BF16>(__uint_as_float(o[8 * v + 6]) * inv_l, __uint_as_float(o[8 * v + 7]) * inv_l);
+            *reinterpret_cast<uint4*>(optr + g * 32 + v * 8) = w;
+          }
+        }
+      }
+      if (row_ok && args.lse) {
+        // natural-log LSE of the scaled scores; -inf for rows that saw no key
+        const float lse = l_run > 0.f ? (m_used * c + log2f(l_run)) * 0.6931471805599453f : -INFINITY;
+        args.lse[static_cast<size_t>(bh) * args.S + out_row] = lse;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::kTmemCols>(tmem);
+  }
+}
+
+}  // namespace svgb

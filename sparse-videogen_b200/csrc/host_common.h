@@ -1,0 +1,51 @@
+// Host-side helpers shared by every translation unit of libsvgb200.so.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+
+namespace svgb {
+
+// thread-local last-error message (api.cu)
+void set_error(const char* fmt, ...);
+const char* get_error();
+
+#define SVGB_REQUIRE(cond, ...)   \
+  do {                            \
+    if (!(cond)) {                \
+      svgb::set_error(__VA_ARGS__); \
+      return -1;                  \
+    }                             \
+  } while (0)
+
+#define SVGB_CUDA(expr)                                                                    \
+  do {                                                                                     \
+    cudaError_t _e = (expr);                                                               \
+    if (_e != cudaSuccess) {                                                               \
+      svgb::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__,    \
+                      __LINE__);                                                           \
+      return -2;                                                                           \
+    }                                                                                      \
+  } while (0)
+
+// check the launch that just happened (no sync)
+#define SVGB_LAUNCH_OK()                                                                   \
+  do {                                                                                     \
+    cudaError_t _e = cudaGetLastError();                                                   \
+    if (_e != cudaSuccess) {                                                               \
+      svgb::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, \
+                      __LINE__);                                                           \
+      return -3;                                                                           \
+    }                                                                                      \
+  } while (0)
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// 3-D TMA descriptor over a [BH, S, D] 16-bit tensor addressed as (d, s, h) with byte strides.
+// box = 64 x 128 x 1, 128-byte swizzle.  Returns 0 on success.
+int encode_tmap_hsd(CUtensorMap* map, const void* base, int dtype, int BH, int S, int D,
+                    long long row_stride_elems, long long head_stride_elems, int box_rows = 128);
+
+}  // namespace svgb
