@@ -114,18 +114,32 @@ int svgb_head_placement(const void* const* in, void* const* out, int n_tensors,
                         int text_first, int inverse, void* stream);
 
 /* ---- flash k-means (svg/kmeans_utils.py:464-733) ------------------------------------------ */
-/* nearest centroid per point: argmin_k max(0, |x|^2 + |c_k|^2 - 2 x.c_k); x,c bf16 [BH,N,D],
- * [BH,K,D]; x_sq float [BH,N]; labels int32 [BH,N].  (_euclid_assign_kernel :464-554) */
+/* one workspace serves assign / update / run for a given (BH, N, K, D); K <= 4096 */
+int svgb_kmeans_bytes(int BH, int N, int K, int D, size_t* bytes);
+/* x_sq[h,n] = sum_d round16(x^2): round_result=1 rounds the sum to the 16-bit dtype as
+ * (x**2).sum(-1) does (batch_kmeans_Euclid :704); 0 keeps the fp32 sum (assign kernel :531) */
+int svgb_row_sqnorm(const void* x, float* x_sq, int BH, int N, int D, int dtype, int round_result,
+                    void* stream);
+/* nearest centroid per point: argmin_k max(0, |x|^2 + |c_k|^2 - 2 x.c_k), lowest k wins ties;
+ * x [BH,N,D], c [BH,K,D] 16-bit; x_sq float [BH,N]; labels int32 [BH,N].
+ * (_euclid_assign_kernel :464-554).  X.C^T runs on tcgen05. */
 int svgb_kmeans_assign(const void* x, const void* c, const float* x_sq, int32_t* labels, int BH,
-                       int N, int K, int D, int dtype, void* stream);
-/* centroid update (triton_centroid_update_sorted_euclid :375-421): fp32 mean of members, empty
- * cluster keeps old centroid; deterministic (no float atomics).  Also returns counts. */
-int svgb_kmeans_update_bytes(int BH, int N, int K, int D, size_t* bytes);
+                       int N, int K, int D, int dtype, void* ws, size_t ws_bytes, void* stream);
+/* centroid update (triton_centroid_update_sorted_euclid :375-421): fp32 mean of members in token
+ * order (deterministic; the reference's atomics are not), empty cluster keeps the old centroid,
+ * result rounded to the 16-bit dtype.  counts int32 [BH,K]; shift_max (optional) float[1] =
+ * max_k |c_new - c_old|_2 evaluated with the reference's 16-bit tensor roundings (:642). */
 int svgb_kmeans_update(const void* x, const int32_t* labels, const void* c_old, void* c_new,
-                       int32_t* counts, float* shift_max /* [1], max_k |dc| */, int BH, int N, int K,
-                       int D, int dtype, void* ws, size_t ws_bytes, void* stream);
-/* x_sq[h,n] = sum_d x^2 computed in the input dtype's rounding (batch_kmeans_Euclid :704) */
-int svgb_row_sqnorm(const void* x, float* x_sq, int BH, int N, int D, int dtype, void* stream);
+                       int32_t* counts, float* shift_max, int BH, int N, int K, int D, int dtype,
+                       void* ws, size_t ws_bytes, void* stream);
+/* batch_kmeans_Euclid (:684-733) as one stream-ordered sequence without host syncs: up to
+ * max_iters x (assign, update), device-side `break` when shift < tol.  Outputs follow the
+ * reference exactly: labels / counts from the last executed assignment; centroids = the updated
+ * ones unless the loop broke, then the ones that assignment was made against.  n_iter_out:
+ * device int32[1] (optional). */
+int svgb_kmeans_run(const void* x, const void* init_centroids, int BH, int N, int K, int D, int dtype,
+                    int max_iters, float tol, int32_t* labels, void* centroids_out, int32_t* counts,
+                    int32_t* n_iter_out, void* ws, size_t ws_bytes, void* stream);
 
 /* ---- mask selection --------------------------------------------------------------------- */
 /* identify_dynamic_map (svg/kmeans_utils.py:864-896): qc [BH,QC,D], kc [BH,KC,D] 16-bit,

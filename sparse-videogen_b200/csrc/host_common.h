@@ -48,4 +48,9 @@ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 int encode_tmap_hsd(CUtensorMap* map, const void* base, int dtype, int BH, int S, int D,
                     long long row_stride_elems, long long head_stride_elems, int box_rows = 128);
 
+// stable counting-sort argsort (layout_ops.cu); `offs` (optional) receives the exclusive prefix of
+// counts per head; `skip_flag` (optional, device) turns the three kernels into no-ops when non-zero.
+int argsort_labels_impl(const int* labels, int BH, int S, int K, int* perm, int* counts, int* offs,
+                        void* ws, const int* skip_flag, cudaStream_t stream);
+
 }  // namespace svgb

@@ -1,0 +1,559 @@
+// flash-k-means for sm_100a (reference: svg/kmeans_utils.py:258-322, 375-421, 464-733).
+//
+//   assign : labels[n] = argmin_k max(0, |x_n|^2 + |c_k|^2 - 2 x_n.c_k).  X.C^T on tcgen05 (256 points
+//            per CTA = two 128-row tiles sharing every centroid tile, double-buffered TMEM accumulators),
+//            fused distance + running argmin epilogue (one thread per point).  Tensor-bound.
+//   update : deterministic segmented mean.  The reference sorts labels and uses fp32 atomics
+//            (non-deterministic order); we reuse the stable counting sort (layout_ops.cu) and sum each
+//            cluster's members in index order.  HBM-bound (x read once).
+//   run    : the whole Lloyd loop on the device, no host sync: a `done` flag turns later iterations
+//            into no-ops and a device-side buffer index replaces the reference's Python swap.
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include "../../include/svgb200.h"
+#include "host_common.h"
+#include "ptx.cuh"
+
+namespace svgb {
+
+// ---------------------------------------------------------------------------------------------
+// squared row norms
+//   round_result=1: (x**2).sum(-1) in the 16-bit dtype (squares rounded, fp32 sum, result rounded)
+//                   -- batch_kmeans_Euclid:704
+//   round_result=0: fp32 sum of 16-bit-rounded squares -- _euclid_assign_kernel:531
+// ---------------------------------------------------------------------------------------------
+template <bool BF16>
+__device__ __forceinline__ float to_f32(uint16_t h) {
+  if constexpr (BF16) return __uint_as_float(static_cast<uint32_t>(h) << 16);
+  else return __half2float(__ushort_as_half(h));
+}
+template <bool BF16>
+__device__ __forceinline__ float round16(float f) {
+  if constexpr (BF16) return __bfloat162float(__float2bfloat16_rn(f));
+  else return __half2float(__float2half_rn(f));
+}
+
+template <bool BF16>
+__global__ void row_sqnorm_kernel(const uint16_t* __restrict__ x, float* __restrict__ out, long long rows,
+                                  int D, int round_result) {
+  // one warp per row; lanes stride the row, fixed-order tree reduction (deterministic)
+  const long long row = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const uint16_t* p = x + row * D;
+  float acc = 0.f;
+  for (int d = lane; d < D; d += 32) {
+    const float v = to_f32<BF16>(p[d]);
+    acc += round16<BF16>(v * v);
+  }
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) out[row] = round_result ? round16<BF16>(acc) : acc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// assign
+// ---------------------------------------------------------------------------------------------
+struct KmState {  // device-resident loop state
+  int done;
+  int cur;     // which centroid buffer the next assignment reads
+  int n_iter;
+  float shift;
+};
+
+template <int D>
+struct AssignCfg {
+  static constexpr int kHalves = D / 64;
+  static constexpr int kPanelBytes = 128 * 128;
+  static constexpr int kTileBytes = kPanelBytes * kHalves;
+  static constexpr int kStages = 4;
+  static constexpr int kXBytes = 2 * kTileBytes;
+  static constexpr int kRingBytes = kStages * kTileBytes;
+  static constexpr int kMaxK = 4096;              // whole |c|^2 row of one head lives in smem
+  static constexpr int kCsqBytes = kMaxK * 4;
+  static constexpr int kSmemBytes = 1024 + kXBytes + kRingBytes + kCsqBytes + 512;
+};
+
+struct AssignBars {
+  uint64_t x_full;
+  uint64_t c_full[4], c_empty[4];
+  uint64_t s_full[2][2], s_empty[2][2];
+  uint32_t tmem_base;
+};
+
+template <int D, bool BF16>
+__global__ void __launch_bounds__(384, 1)
+kmeans_assign_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap cmap0,
+                     const __grid_constant__ CUtensorMap cmap1, const float* __restrict__ x_sq,
+                     const float* __restrict__ c_sq, int* __restrict__ labels, int N, int K,
+                     const KmState* __restrict__ state) {
+  using Cfg = AssignCfg<D>;
+  int cur = 0;
+  if (state) {
+    if (state->done) return;
+    cur = state->cur;
+  }
+  const CUtensorMap* cmap = cur == 0 ? &cmap0 : &cmap1;
+  const int bh = blockIdx.y;
+  const int row0 = blockIdx.x * 256;
+  const int ntiles = (N - row0) > 128 ? 2 : 1;
+  const int nchunks = (K + 127) / 128;
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t sX = smem_base, sRing = smem_base + Cfg::kXBytes;
+  float* csq = reinterpret_cast<float*>(smem_al + Cfg::kXBytes + Cfg::kRingBytes);
+  AssignBars* bars = reinterpret_cast<AssignBars*>(smem_al + Cfg::kXBytes + Cfg::kRingBytes + Cfg::kCsqBytes);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&xmap);
+    tma_prefetch_desc(cmap);
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(smem_u32(&bars->x_full), 1);
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      mbar_init(smem_u32(&bars->c_full[s]), 1);
+      mbar_init(smem_u32(&bars->c_empty[s]), 1);
+    }
+    for (int t = 0; t < 2; ++t)
+      for (int b = 0; b < 2; ++b) {
+        mbar_init(smem_u32(&bars->s_full[t][b]), 1);
+        mbar_init(smem_u32(&bars->s_empty[t][b]), 128);
+      }
+    mbar_fence_init();
+  }
+  if (warp == 2) tmem_alloc<512>(smem_u32(&bars->tmem_base));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = bars->tmem_base;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint32_t xb = smem_u32(&bars->x_full);
+      mbar_expect_tx(xb, ntiles * Cfg::kTileBytes + nchunks * 512);
+      for (int t = 0; t < ntiles; ++t)
+        for (int h = 0; h < Cfg::kHalves; ++h)
+          tma_load_3d(sX + t * Cfg::kTileBytes + h * Cfg::kPanelBytes, &xmap, xb, h * 64, row0 + t * 128, bh);
+      // |c|^2 of the whole head (padded to a multiple of 128 floats) rides the same barrier
+      asm volatile(
+          "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+          ::"r"(smem_u32(csq)), "l"(c_sq + static_cast<size_t>(bh) * nchunks * 128), "r"(nchunks * 512),
+          "r"(xb)
+          : "memory");
+      for (int j = 0; j < nchunks; ++j) {
+        const int slot = j % Cfg::kStages;
+        mbar_wait(smem_u32(&bars->c_empty[slot]), ((j / Cfg::kStages) & 1) ^ 1, 31);
+        const uint32_t fb = smem_u32(&bars->c_full[slot]);
+        mbar_expect_tx(fb, Cfg::kTileBytes);
+        for (int h = 0; h < Cfg::kHalves; ++h)
+          tma_load_3d(sRing + slot * Cfg::kTileBytes + h * Cfg::kPanelBytes, cmap, fb, h * 64, j * 128, bh);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      mbar_wait(smem_u32(&bars->x_full), 0, 32);
+      const uint32_t idesc = make_idesc(128, 128, BF16, false, false);
+      for (int j = 0; j < nchunks; ++j) {
+        const int slot = j % Cfg::kStages, buf = j & 1;
+        mbar_wait(smem_u32(&bars->c_full[slot]), (j / Cfg::kStages) & 1, 33);
+        for (int t = 0; t < ntiles; ++t) {
+          mbar_wait(smem_u32(&bars->s_empty[t][buf]), ((j >> 1) & 1) ^ 1, 34);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem + t * 256 + buf * 128;
+#pragma unroll
+          for (int kk = 0; kk < D / 16; ++kk) {
+            const uint32_t off = (kk >> 2) * Cfg::kPanelBytes + (kk & 3) * 32;
+            mma_ss(d_tmem, desc_kmajor_sw128(sX + t * Cfg::kTileBytes + off),
+                   desc_kmajor_sw128(sRing + slot * Cfg::kTileBytes + off), idesc, kk > 0);
+          }
+          tc_commit(smem_u32(&bars->s_full[t][buf]));
+        }
+        tc_commit(smem_u32(&bars->c_empty[slot]));
+      }
+    }
+  } else if (warp >= 4) {
+    const int t = (warp - 4) >> 2;
+    if (t < ntiles) {
+      const int wq = warp & 3;
+      const int n = row0 + t * 128 + wq * 32 + lane;
+      const uint32_t lane_addr = tmem + (static_cast<uint32_t>(wq * 32) << 16) + t * 256;
+      const float xs = (n < N) ? x_sq[static_cast<size_t>(bh) * N + n] : 0.f;
+      float best = 3.4e38f;
+      int best_k = 0;
+      mbar_wait(smem_u32(&bars->x_full), 0, 35);  // |c|^2 row landed with X
+      for (int j = 0; j < nchunks; ++j) {
+        const int buf = j & 1;
+        mbar_wait(smem_u32(&bars->s_full[t][buf]), (j >> 1) & 1, 36);
+        tc_fence_after();
+        const float* cs = csq + j * 128;
+        const int kbase = j * 128;
+#pragma unroll 1
+        for (int g = 0; g < 4; ++g) {
+          uint32_t r[32];
+          tmem_ld32(lane_addr + buf * 128 + g * 32, r);
+          tc_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int kidx = kbase + g * 32 + i;
+            float d = fmaf(-2.f, __uint_as_float(r[i]), xs + cs[g * 32 + i]);
+            d = fmaxf(d, 0.f);
+            if (kidx >= K) d = 3.4e38f;
+            if (d < best) {
+              best = d;
+              best_k = kidx;
+            }
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(smem_u32(&bars->s_empty[t][buf]));
+      }
+      if (n < N) labels[static_cast<size_t>(bh) * N + n] = best_k;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// update: one CTA per (head, cluster); members = perm[off .. off+cnt) (ascending token index)
+// 256 threads = 4 row-groups x 64 threads (2 dims each, D=128) ; fixed-order combine
+// ---------------------------------------------------------------------------------------------
+template <bool BF16>
+__global__ void __launch_bounds__(256)
+kmeans_update_kernel(const uint16_t* __restrict__ x, const int* __restrict__ perm,
+                     const int* __restrict__ counts, const int* __restrict__ chunk0_base,
+                     const uint16_t* __restrict__ c_old0, const uint16_t* __restrict__ c_old1,
+                     uint16_t* __restrict__ c_new0, uint16_t* __restrict__ c_new1, float* __restrict__ shift_max,
+                     int N, int K, int D, const KmState* __restrict__ state) {
+  int cur = 0;
+  if (state) {
+    if (state->done) return;
+    cur = state->cur;
+  }
+  const uint16_t* c_old = cur == 0 ? c_old0 : c_old1;
+  uint16_t* c_new = cur == 0 ? c_new0 : c_new1;
+  const int k = blockIdx.x, bh = blockIdx.y;
+  const int cnt = counts[static_cast<size_t>(bh) * K + k];
+  const int off = chunk0_base[static_cast<size_t>(bh) * K + k];  // exclusive prefix of counts
+  const int dpairs = D / 2;                                       // 32-bit words per row
+  const int groups = blockDim.x / dpairs;
+  const int grp = threadIdx.x / dpairs, w = threadIdx.x % dpairs;
+  __shared__ float2 part[8][64];
+  __shared__ float s_norm[64];
+  float2 acc = make_float2(0.f, 0.f);
+  if (grp < groups) {
+    const int* pp = perm + static_cast<size_t>(bh) * N + off;
+    const uint32_t* xb = reinterpret_cast<const uint32_t*>(x) + static_cast<size_t>(bh) * N * dpairs;
+    int i = grp;
+    for (; i + 3 * groups < cnt; i += 4 * groups) {
+      uint32_t v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = __ldg(xb + static_cast<size_t>(__ldg(pp + i + u * groups)) * dpairs + w);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        acc.x += to_f32<BF16>(static_cast<uint16_t>(v[u] & 0xffff));
+        acc.y += to_f32<BF16>(static_cast<uint16_t>(v[u] >> 16));
+      }
+    }
+    for (; i < cnt; i += groups) {
+      const uint32_t v = __ldg(xb + static_cast<size_t>(__ldg(pp + i)) * dpairs + w);
+      acc.x += to_f32<BF16>(static_cast<uint16_t>(v & 0xffff));
+      acc.y += to_f32<BF16>(static_cast<uint16_t>(v >> 16));
+    }
+    part[grp][w] = acc;
+  }
+  __syncthreads();
+  if (threadIdx.x < dpairs) {
+    float2 s = make_float2(0.f, 0.f);
+    for (int gI = 0; gI < groups; ++gI) {
+      s.x += part[gI][w].x;
+      s.y += part[gI][w].y;
+    }
+    const uint32_t oldw = reinterpret_cast<const uint32_t*>(c_old)[(static_cast<size_t>(bh) * K + k) * dpairs + w];
+    const float o0 = to_f32<BF16>(static_cast<uint16_t>(oldw & 0xffff));
+    const float o1 = to_f32<BF16>(static_cast<uint16_t>(oldw >> 16));
+    float n0, n1;
+    if (cnt > 0) {
+      const float denom = static_cast<float>(cnt);
+      n0 = round16<BF16>(s.x / denom);
+      n1 = round16<BF16>(s.y / denom);
+    } else {
+      n0 = o0;
+      n1 = o1;
+    }
+    uint32_t packed;
+    if constexpr (BF16) {
+      packed = (__float_as_uint(n0) >> 16) | (__float_as_uint(n1) & 0xffff0000u);
+    } else {
+      packed = static_cast<uint32_t>(__half_as_ushort(__float2half_rn(n0))) |
+               (static_cast<uint32_t>(__half_as_ushort(__float2half_rn(n1))) << 16);
+    }
+    reinterpret_cast<uint32_t*>(c_new)[(static_cast<size_t>(bh) * K + k) * dpairs + w] = packed;
+    // shift = |round16(new - old)|_2, then rounded to 16 bit like the reference's bf16 tensor ops
+    const float d0 = round16<BF16>(n0 - o0), d1 = round16<BF16>(n1 - o1);
+    s_norm[w] = d0 * d0 + d1 * d1;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && shift_max) {
+    float t = 0.f;
+    for (int i = 0; i < dpairs; ++i) t += s_norm[i];
+    const float nrm = round16<BF16>(sqrtf(t));
+    atomicMax(reinterpret_cast<int*>(shift_max), __float_as_int(nrm));  // non-negative floats order as ints
+  }
+}
+
+// |c|^2 of the centroid buffer selected by the loop state, written in the padded [BH, Kpad] layout
+// the assign kernel bulk-copies (fp32 sum of 16-bit-rounded squares, _euclid_assign_kernel:531).
+template <bool BF16>
+__global__ void csq_kernel(const uint16_t* __restrict__ c0, const uint16_t* __restrict__ c1,
+                           float* __restrict__ out, int K, int Kpad, int D, const KmState* __restrict__ state) {
+  int cur = 0;
+  if (state) {
+    if (state->done) return;
+    cur = state->cur;
+  }
+  const uint16_t* c = cur == 0 ? c0 : c1;
+  const int bh = blockIdx.y;
+  const int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (k >= Kpad) return;
+  float acc = 0.f;
+  if (k < K) {
+    const uint16_t* p = c + (static_cast<size_t>(bh) * K + k) * D;
+    for (int d = lane; d < D; d += 32) {
+      const float v = to_f32<BF16>(p[d]);
+      acc += round16<BF16>(v * v);
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) out[static_cast<size_t>(bh) * Kpad + k] = acc;
+}
+
+__global__ void km_commit_kernel(KmState* st, float* shift_max, float tol, int it) {
+  if (st->done) return;
+  const float sh = *shift_max;
+  st->shift = sh;
+  st->n_iter = it + 1;
+  if (sh < tol) st->done = 1;  // break BEFORE `centroids = centroids_new` (kmeans_utils.py:723-726)
+  else st->cur ^= 1;
+  *shift_max = 0.f;
+}
+
+__global__ void km_init_state_kernel(KmState* st, float* shift_max) {
+  st->done = 0;
+  st->cur = 0;
+  st->n_iter = 0;
+  st->shift = 0.f;
+  *shift_max = 0.f;
+}
+
+// copy the final centroids (buffer `cur`) and n_iter out
+__global__ void km_finalize_kernel(const KmState* st, const uint4* __restrict__ c0, const uint4* __restrict__ c1,
+                                   uint4* __restrict__ out, long long n_vec, int* __restrict__ n_iter_out) {
+  const uint4* src = st->cur == 0 ? c0 : c1;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n_vec;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    out[i] = src[i];
+  if (n_iter_out && blockIdx.x == 0 && threadIdx.x == 0) *n_iter_out = st->n_iter;
+}
+
+template <int D, bool BF16>
+static int launch_assign(const CUtensorMap& xm, const CUtensorMap& cm0, const CUtensorMap& cm1,
+                         const float* x_sq, const float* c_sq_padded, int* labels, int BH, int N, int K,
+                         const KmState* st, cudaStream_t stream) {
+  using Cfg = AssignCfg<D>;
+  auto kern = kmeans_assign_kernel<D, BF16>;
+  SVGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+  dim3 grid((N + 255) / 256, BH);
+  kern<<<grid, 384, Cfg::kSmemBytes, stream>>>(xm, cm0, cm1, x_sq, c_sq_padded, labels, N, K, st);
+  SVGB_LAUNCH_OK();
+  return 0;
+}
+
+static int dispatch_assign(const void* x, const void* c0, const void* c1, const float* x_sq,
+                           const float* c_sq_padded, int* labels, int BH, int N, int K, int D, int dtype,
+                           const KmState* st, cudaStream_t stream) {
+  CUtensorMap xm, cm0, cm1;
+  if (encode_tmap_hsd(&xm, x, dtype, BH, N, D, D, static_cast<long long>(N) * D)) return -1;
+  if (encode_tmap_hsd(&cm0, c0, dtype, BH, K, D, D, static_cast<long long>(K) * D)) return -1;
+  if (encode_tmap_hsd(&cm1, c1, dtype, BH, K, D, D, static_cast<long long>(K) * D)) return -1;
+  if (D == 128)
+    return dtype == SVGB_BF16 ? launch_assign<128, true>(xm, cm0, cm1, x_sq, c_sq_padded, labels, BH, N, K, st, stream)
+                              : launch_assign<128, false>(xm, cm0, cm1, x_sq, c_sq_padded, labels, BH, N, K, st, stream);
+  return dtype == SVGB_BF16 ? launch_assign<64, true>(xm, cm0, cm1, x_sq, c_sq_padded, labels, BH, N, K, st, stream)
+                            : launch_assign<64, false>(xm, cm0, cm1, x_sq, c_sq_padded, labels, BH, N, K, st, stream);
+}
+
+static int launch_sqnorm(const void* x, float* out, long long rows, int D, int dtype, int round_result,
+                         cudaStream_t stream) {
+  const int block = 256;
+  const long long blocks = (rows * 32 + block - 1) / block;
+  if (dtype == SVGB_BF16)
+    row_sqnorm_kernel<true><<<static_cast<unsigned>(blocks), block, 0, stream>>>(
+        static_cast<const uint16_t*>(x), out, rows, D, round_result);
+  else
+    row_sqnorm_kernel<false><<<static_cast<unsigned>(blocks), block, 0, stream>>>(
+        static_cast<const uint16_t*>(x), out, rows, D, round_result);
+  SVGB_LAUNCH_OK();
+  return 0;
+}
+
+static int launch_csq(const void* c0, const void* c1, float* out, int BH, int K, int D, int dtype,
+                      const KmState* st, cudaStream_t stream) {
+  const int Kpad = (K + 127) / 128 * 128;
+  dim3 grid((Kpad * 32 + 255) / 256, BH);
+  if (dtype == SVGB_BF16)
+    csq_kernel<true><<<grid, 256, 0, stream>>>(static_cast<const uint16_t*>(c0), static_cast<const uint16_t*>(c1),
+                                               out, K, Kpad, D, st);
+  else
+    csq_kernel<false><<<grid, 256, 0, stream>>>(static_cast<const uint16_t*>(c0), static_cast<const uint16_t*>(c1),
+                                                out, K, Kpad, D, st);
+  SVGB_LAUNCH_OK();
+  return 0;
+}
+
+static int launch_update(const void* x, const int* perm, const int* counts, const int* offs, const void* c_old0,
+                         const void* c_old1, void* c_new0, void* c_new1, float* shift_max, int BH, int N, int K,
+                         int D, int dtype, const KmState* st, cudaStream_t stream) {
+  dim3 grid(K, BH);
+  const int threads = 2 * D;  // 4 row-groups of D/2 threads
+  auto X = static_cast<const uint16_t*>(x);
+  auto O0 = static_cast<const uint16_t*>(c_old0);
+  auto O1 = static_cast<const uint16_t*>(c_old1);
+  auto N0 = static_cast<uint16_t*>(c_new0);
+  auto N1 = static_cast<uint16_t*>(c_new1);
+  if (dtype == SVGB_BF16)
+    kmeans_update_kernel<true><<<grid, threads, 0, stream>>>(X, perm, counts, offs, O0, O1, N0, N1, shift_max, N, K, D, st);
+  else
+    kmeans_update_kernel<false><<<grid, threads, 0, stream>>>(X, perm, counts, offs, O0, O1, N0, N1, shift_max, N, K, D, st);
+  SVGB_LAUNCH_OK();
+  return 0;
+}
+
+struct KmLayout {
+  size_t csq_pad, perm, offs, sort, sort_bytes, cbuf0, cbuf1, state, xsq, total;
+};
+static KmLayout km_layout(int BH, int N, int K, int D) {
+  KmLayout L;
+  size_t o = 0;
+  auto take = [&](size_t bytes) {
+    size_t at = o;
+    o += align_up(bytes, 256);
+    return at;
+  };
+  const int Kpad = (K + 127) / 128 * 128;
+  L.csq_pad = take(sizeof(float) * BH * Kpad);
+  L.perm = take(sizeof(int) * static_cast<size_t>(BH) * N);
+  L.offs = take(sizeof(int) * BH * K);
+  L.sort_bytes = 0;
+  svgb_argsort_labels_bytes(BH, N, K, &L.sort_bytes);
+  L.sort = take(L.sort_bytes);
+  L.cbuf0 = take(2ull * BH * K * D);
+  L.cbuf1 = take(2ull * BH * K * D);
+  L.state = take(256);
+  L.xsq = take(sizeof(float) * static_cast<size_t>(BH) * N);
+  L.total = o;
+  return L;
+}
+
+}  // namespace svgb
+
+using namespace svgb;
+
+extern "C" {
+
+int svgb_row_sqnorm(const void* x, float* x_sq, int BH, int N, int D, int dtype, int round_result,
+                    void* stream) {
+  SVGB_REQUIRE(x && x_sq && BH > 0 && N > 0 && D > 0, "bad arguments");
+  SVGB_REQUIRE(dtype == SVGB_BF16 || dtype == SVGB_F16, "dtype %d unsupported", dtype);
+  return launch_sqnorm(x, x_sq, static_cast<long long>(BH) * N, D, dtype, round_result,
+                       static_cast<cudaStream_t>(stream));
+}
+
+int svgb_kmeans_bytes(int BH, int N, int K, int D, size_t* bytes) {
+  SVGB_REQUIRE(BH > 0 && N > 0 && K > 0 && K <= 4096 && (D == 64 || D == 128) && bytes,
+               "bad arguments (need K <= 4096, D in {64,128})");
+  *bytes = km_layout(BH, N, K, D).total;
+  return 0;
+}
+
+int svgb_kmeans_assign(const void* x, const void* c, const float* x_sq, int32_t* labels, int BH, int N,
+                       int K, int D, int dtype, void* ws, size_t ws_bytes, void* stream) {
+  SVGB_REQUIRE(x && c && x_sq && labels && ws, "null pointer");
+  size_t need = 0;
+  if (svgb_kmeans_bytes(BH, N, K, D, &need)) return -1;
+  SVGB_REQUIRE(ws_bytes >= need, "workspace too small: %zu < %zu", ws_bytes, need);
+  const KmLayout L = km_layout(BH, N, K, D);
+  char* w = static_cast<char*>(ws);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float* csqp = reinterpret_cast<float*>(w + L.csq_pad);
+  if (launch_csq(c, c, csqp, BH, K, D, dtype, nullptr, st)) return -1;
+  return dispatch_assign(x, c, c, x_sq, csqp, labels, BH, N, K, D, dtype, nullptr, st);
+}
+
+int svgb_kmeans_update(const void* x, const int32_t* labels, const void* c_old, void* c_new,
+                       int32_t* counts, float* shift_max, int BH, int N, int K, int D, int dtype,
+                       void* ws, size_t ws_bytes, void* stream) {
+  SVGB_REQUIRE(x && labels && c_old && c_new && counts && ws, "null pointer");
+  size_t need = 0;
+  if (svgb_kmeans_bytes(BH, N, K, D, &need)) return -1;
+  SVGB_REQUIRE(ws_bytes >= need, "workspace too small: %zu < %zu", ws_bytes, need);
+  const KmLayout L = km_layout(BH, N, K, D);
+  char* w = static_cast<char*>(ws);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int* perm = reinterpret_cast<int*>(w + L.perm);
+  int* offs = reinterpret_cast<int*>(w + L.offs);
+  if (argsort_labels_impl(labels, BH, N, K, perm, counts, offs, w + L.sort, nullptr, st)) return -1;
+  if (shift_max) SVGB_CUDA(cudaMemsetAsync(shift_max, 0, sizeof(float), st));
+  return launch_update(x, perm, counts, offs, c_old, c_old, c_new, c_new, shift_max, BH, N, K, D, dtype, nullptr, st);
+}
+
+int svgb_kmeans_run(const void* x, const void* init_centroids, int BH, int N, int K, int D, int dtype,
+                    int max_iters, float tol, int32_t* labels, void* centroids_out, int32_t* counts,
+                    int32_t* n_iter_out, void* ws, size_t ws_bytes, void* stream) {
+  SVGB_REQUIRE(x && init_centroids && labels && centroids_out && counts && ws, "null pointer");
+  SVGB_REQUIRE(max_iters >= 1, "max_iters must be >= 1");
+  size_t need = 0;
+  if (svgb_kmeans_bytes(BH, N, K, D, &need)) return -1;
+  SVGB_REQUIRE(ws_bytes >= need, "workspace too small: %zu < %zu", ws_bytes, need);
+  const KmLayout L = km_layout(BH, N, K, D);
+  char* w = static_cast<char*>(ws);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float* csqp = reinterpret_cast<float*>(w + L.csq_pad);
+  int* perm = reinterpret_cast<int*>(w + L.perm);
+  int* offs = reinterpret_cast<int*>(w + L.offs);
+  void* cb0 = w + L.cbuf0;
+  void* cb1 = w + L.cbuf1;
+  KmState* state = reinterpret_cast<KmState*>(w + L.state);
+  float* shift = reinterpret_cast<float*>(w + L.state + 64);
+  float* x_sq = reinterpret_cast<float*>(w + L.xsq);
+
+  km_init_state_kernel<<<1, 1, 0, st>>>(state, shift);
+  SVGB_LAUNCH_OK();
+  SVGB_CUDA(cudaMemcpyAsync(cb0, init_centroids, 2ull * BH * K * D, cudaMemcpyDeviceToDevice, st));
+  if (launch_sqnorm(x, x_sq, static_cast<long long>(BH) * N, D, dtype, 1, st)) return -1;
+  for (int it = 0; it < max_iters; ++it) {
+    // every kernel of an iteration is a no-op once state->done is set (device-side `break`)
+    if (launch_csq(cb0, cb1, csqp, BH, K, D, dtype, state, st)) return -1;
+    if (dispatch_assign(x, cb0, cb1, x_sq, csqp, labels, BH, N, K, D, dtype, state, st)) return -1;
+    if (argsort_labels_impl(labels, BH, N, K, perm, counts, offs, w + L.sort, &state->done, st)) return -1;
+    // update reads buffer `cur`, writes the other one
+    if (launch_update(x, perm, counts, offs, cb0, cb1, cb1, cb0, shift, BH, N, K, D, dtype, state, st)) return -1;
+    km_commit_kernel<<<1, 1, 0, st>>>(state, shift, tol, it);
+    SVGB_LAUNCH_OK();
+  }
+  const long long n_vec = 2ll * BH * K * D / 16;
+  km_finalize_kernel<<<64, 256, 0, st>>>(state, static_cast<const uint4*>(cb0), static_cast<const uint4*>(cb1),
+                                         static_cast<uint4*>(centroids_out), n_vec, n_iter_out);
+  SVGB_LAUNCH_OK();
+  return 0;
+}
+
+}  // extern "C"

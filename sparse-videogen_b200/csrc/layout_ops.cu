@@ -114,8 +114,9 @@ head_placement_kernel(PlacementPtrs ptrs, const int* __restrict__ best_mask_idx,
 constexpr int kSortChunk = 1024;
 
 __global__ void sort_hist_kernel(const int* __restrict__ labels, int S, int K, int n_chunks,
-                                 int* __restrict__ hist) {
+                                 int* __restrict__ hist, const int* __restrict__ skip) {
   extern __shared__ int sh[];
+  if (skip && *skip) return;
   const int h = blockIdx.y, c = blockIdx.x;
   for (int k = threadIdx.x; k < K; k += blockDim.x) sh[k] = 0;
   __syncthreads();
@@ -129,8 +130,10 @@ __global__ void sort_hist_kernel(const int* __restrict__ labels, int S, int K, i
   for (int k = threadIdx.x; k < K; k += blockDim.x) dst[k] = sh[k];
 }
 
-__global__ void sort_scan_kernel(int K, int n_chunks, int* __restrict__ hist, int* __restrict__ counts) {
+__global__ void sort_scan_kernel(int K, int n_chunks, int* __restrict__ hist, int* __restrict__ counts,
+                                 int* __restrict__ offs, const int* __restrict__ skip) {
   extern __shared__ int sh[];  // K totals -> exclusive offsets
+  if (skip && *skip) return;
   const int h = blockIdx.x;
   int* base = hist + static_cast<long long>(h) * n_chunks * K;
   for (int k = threadIdx.x; k < K; k += blockDim.x) {
@@ -155,14 +158,16 @@ __global__ void sort_scan_kernel(int K, int n_chunks, int* __restrict__ hist, in
   __syncthreads();
   for (int k = threadIdx.x; k < K; k += blockDim.x) {
     const int off = sh[k];
+    if (offs) offs[static_cast<long long>(h) * K + k] = off;
     for (int c = 0; c < n_chunks; ++c) base[static_cast<long long>(c) * K + k] += off;
   }
 }
 
 __global__ void __launch_bounds__(32)
 sort_place_kernel(const int* __restrict__ labels, int S, int K, int n_chunks,
-                  const int* __restrict__ hist, int* __restrict__ perm) {
+                  const int* __restrict__ hist, int* __restrict__ perm, const int* __restrict__ skip) {
   extern __shared__ int cnt[];  // running position per cluster for this chunk
+  if (skip && *skip) return;
   const int h = blockIdx.y, c = blockIdx.x, lane = threadIdx.x;
   const int* base = hist + (static_cast<long long>(h) * n_chunks + c) * K;
   for (int k = lane; k < K; k += 32) cnt[k] = base[k];
@@ -190,6 +195,20 @@ static int grid_for(long long work_items, int block) {
   if (g > cap) g = cap;
   if (g < 1) g = 1;
   return static_cast<int>(g);
+}
+
+int argsort_labels_impl(const int* labels, int BH, int S, int K, int* perm, int* counts, int* offs,
+                        void* ws, const int* skip_flag, cudaStream_t st) {
+  SVGB_REQUIRE(K * sizeof(int) <= 48 * 1024, "K=%d too large", K);
+  const int n_chunks = (S + kSortChunk - 1) / kSortChunk;
+  int* hist = static_cast<int*>(ws);
+  sort_hist_kernel<<<dim3(n_chunks, BH), 256, K * sizeof(int), st>>>(labels, S, K, n_chunks, hist, skip_flag);
+  SVGB_LAUNCH_OK();
+  sort_scan_kernel<<<BH, 256, K * sizeof(int), st>>>(K, n_chunks, hist, counts, offs, skip_flag);
+  SVGB_LAUNCH_OK();
+  sort_place_kernel<<<dim3(n_chunks, BH), 32, K * sizeof(int), st>>>(labels, S, K, n_chunks, hist, perm, skip_flag);
+  SVGB_LAUNCH_OK();
+  return 0;
 }
 
 }  // namespace svgb
@@ -256,17 +275,8 @@ int svgb_argsort_labels(const int32_t* labels, int BH, int S, int K, int32_t* pe
   if (svgb_argsort_labels_bytes(BH, S, K, &need)) return -1;
   SVGB_REQUIRE(labels && perm && ws, "null pointer");
   SVGB_REQUIRE(ws_bytes >= need, "workspace too small: %zu < %zu", ws_bytes, need);
-  SVGB_REQUIRE(K * sizeof(int) <= 48 * 1024, "K=%d too large", K);
-  const int n_chunks = (S + kSortChunk - 1) / kSortChunk;
-  int* hist = static_cast<int*>(ws);
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  sort_hist_kernel<<<dim3(n_chunks, BH), 256, K * sizeof(int), st>>>(labels, S, K, n_chunks, hist);
-  SVGB_LAUNCH_OK();
-  sort_scan_kernel<<<BH, 256, K * sizeof(int), st>>>(K, n_chunks, hist, counts);
-  SVGB_LAUNCH_OK();
-  sort_place_kernel<<<dim3(n_chunks, BH), 32, K * sizeof(int), st>>>(labels, S, K, n_chunks, hist, perm);
-  SVGB_LAUNCH_OK();
-  return 0;
+  return argsort_labels_impl(labels, BH, S, K, perm, counts, nullptr, ws, nullptr,
+                             static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"
