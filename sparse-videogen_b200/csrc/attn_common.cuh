@@ -34,6 +34,14 @@ enum MaskMode : int {
   // CogVideoX (text first), reference svg/models/cog/utils.py:30-46
   //   m0 = first-column limit (prompt_len or prompt_len + P), m1 = prompt_len, m2 = W
   MASK_COG = 3,
+  // SVG1 profiling masks of get_attention_mask (hyvideo/utils.py:47-93, wan/utils.py:63-110),
+  // evaluated analytically: 128-token-block band |bq - bk| < thres in frame-major (spatial) or
+  // token-major (temporal) order.  m0 = F, m1 = P, m2 = thres (blocks).  HY: text rows / columns
+  // (index >= F*P) always attend; WAN: first-frame sink painted before the token-major permutation.
+  MASK_PROF_HY_S = 4,
+  MASK_PROF_HY_T = 5,
+  MASK_PROF_WAN_S = 6,
+  MASK_PROF_WAN_T = 7,
 };
 
 __host__ __device__ inline bool mask_allowed(int mode, int q, int kv, int m0, int m1, int m2) {
@@ -50,6 +58,20 @@ __host__ __device__ inline bool mask_allowed(int mode, int q, int kv, int m0, in
       return (kv < m0) || (d <= m2);
     case MASK_COG:
       return (kv < m0) || (q < m1) || (d < m2);
+    case MASK_PROF_HY_S:
+    case MASK_PROF_HY_T:
+    case MASK_PROF_WAN_S:
+    case MASK_PROF_WAN_T: {
+      const int F = m0, P = m1, V = m0 * m1;
+      const bool hy = mode <= MASK_PROF_HY_T;
+      const bool temporal = (mode == MASK_PROF_HY_T) || (mode == MASK_PROF_WAN_T);
+      if (q >= V || kv >= V) return hy;  // text rows / columns (HY); cannot occur for WAN (S == V)
+      const int qi = temporal ? (q % P) * F + q / P : q;
+      const int ki = temporal ? (kv % P) * F + kv / P : kv;
+      int bd = qi / 128 - ki / 128;
+      bd = bd < 0 ? -bd : bd;
+      return (bd < m2) || (!hy && ki < P);
+    }
     default:
       return true;
   }
@@ -67,8 +89,10 @@ struct AttnArgs {
   const int* o_rows;        // optional [BH, S]: output row for query row q (fused inverse permutation)
   float* lse;               // optional [BH, S] (natural log), indexed like o rows
   float scale_log2;         // softmax scale * log2(e)
-  int S;
+  int S;                    // query rows per head (indexing of o_rows / lse / q_index)
   int mask_mode, m0, m1, m2;
+  const int* q_index;       // optional [S]: query position used by the element mask (sampled rows)
+  int out_f32;              // 1: o is fp32 (used for split-KV partials)
 };
 
 }  // namespace svgb

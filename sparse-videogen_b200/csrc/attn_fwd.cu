@@ -272,6 +272,24 @@ static int launch_selftest(const CUtensorMap& qm, const CUtensorMap& km, const C
   return 0;
 }
 
+int attn_fwd_impl(const void* q, int Sq, long long q_rs, long long q_hs, const void* k, const void* v, int Skv,
+                  long long kv_rs, long long kv_hs, int dtype, int BH, int D, const AttnArgs& a, int grid_x,
+                  cudaStream_t st) {
+  SVGB_REQUIRE(D == 64 || D == 128, "head_dim %d unsupported (64 or 128)", D);
+  SVGB_REQUIRE(dtype == SVGB_BF16 || dtype == SVGB_F16, "dtype %d unsupported", dtype);
+  CUtensorMap qm, km, vm;
+  if (encode_tmap_hsd(&qm, q, dtype, BH, Sq, D, q_rs, q_hs)) return -1;
+  if (encode_tmap_hsd(&km, k, dtype, BH, Skv, D, kv_rs, kv_hs)) return -1;
+  if (encode_tmap_hsd(&vm, v, dtype, BH, Skv, D, kv_rs, kv_hs)) return -1;
+  dim3 grid(grid_x, BH);
+  if (D == 128) {
+    return dtype == SVGB_BF16 ? launch_attn<128, true>(qm, km, vm, a, grid, st)
+                              : launch_attn<128, false>(qm, km, vm, a, grid, st);
+  }
+  return dtype == SVGB_BF16 ? launch_attn<64, true>(qm, km, vm, a, grid, st)
+                            : launch_attn<64, false>(qm, km, vm, a, grid, st);
+}
+
 static int varblock_chunk_cap(int S, int KC) { return S / kChunkCols + (KC + 1) / 2 + 2; }
 static int varblock_max_items(int S, int QC) { return S / kItemRows + QC + 1; }
 
@@ -374,10 +392,6 @@ int svgb_attn_fwd(const void* q, const void* k, const void* v, void* o, float* l
                "plan was built for BH=%d S=%d, called with BH=%d S=%d", plan->BH, plan->S, BH, S);
   SVGB_REQUIRE((reinterpret_cast<uintptr_t>(o) & 15) == 0 && o_row_stride % 8 == 0 && o_head_stride % 8 == 0,
                "output must be 16-byte aligned with strides multiple of 8 elements");
-  CUtensorMap qm, km, vm;
-  if (encode_tmap_hsd(&qm, q, dtype, BH, S, D, row_stride, head_stride)) return -1;
-  if (encode_tmap_hsd(&km, k, dtype, BH, S, D, row_stride, head_stride)) return -1;
-  if (encode_tmap_hsd(&vm, v, dtype, BH, S, D, row_stride, head_stride)) return -1;
   const char* ws = static_cast<const char*>(plan_ws);
   AttnArgs a;
   a.items = reinterpret_cast<const int4*>(ws + plan->items_off);
@@ -396,14 +410,10 @@ int svgb_attn_fwd(const void* q, const void* k, const void* v, void* o, float* l
   a.m0 = plan->m0;
   a.m1 = plan->m1;
   a.m2 = plan->m2;
-  dim3 grid(plan->max_items, BH);
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (D == 128) {
-    return dtype == SVGB_BF16 ? launch_attn<128, true>(qm, km, vm, a, grid, st)
-                              : launch_attn<128, false>(qm, km, vm, a, grid, st);
-  }
-  return dtype == SVGB_BF16 ? launch_attn<64, true>(qm, km, vm, a, grid, st)
-                            : launch_attn<64, false>(qm, km, vm, a, grid, st);
+  a.q_index = nullptr;
+  a.out_f32 = 0;
+  return attn_fwd_impl(q, S, row_stride, head_stride, k, v, S, row_stride, head_stride, dtype, BH, D, a,
+                       plan->max_items, static_cast<cudaStream_t>(stream));
 }
 
 int svgb_density(const uint8_t* map, const int32_t* row_sz, const int32_t* col_sz, int BH, int QC,

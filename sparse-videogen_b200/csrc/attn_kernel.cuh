@@ -214,6 +214,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
       const int wq = warp & 3;
       const int row = wq * 32 + lane;  // row inside the 128-row tile == TMEM lane
       const int q = q_row0 + t * kTileRows + row;
+      const int qm = (args.q_index && q < args.S) ? __ldg(&args.q_index[q]) : q;  // position seen by the mask
       const uint32_t lane_addr = tmem + (static_cast<uint32_t>(wq * 32) << 16);
       const uint32_t s_addr = lane_addr + (t == 0 ? Cfg::kSCol0 : Cfg::kSCol1);
       const uint32_t o_addr = lane_addr + (t == 0 ? Cfg::kOCol0 : Cfg::kOCol1);
@@ -249,7 +250,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
           if (elem) {
 #pragma unroll
             for (int i = 0; i < 32; ++i)
-              if (!mask_allowed(mode, q, kv0 + g * 32 + i, m0, m1, m2)) r[i] = 0xff800000u;
+              if (!mask_allowed(mode, qm, kv0 + g * 32 + i, m0, m1, m2)) r[i] = 0xff800000u;
           }
         };
 
@@ -313,6 +314,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
       if (row_ok && args.o_rows) out_row = __ldg(&args.o_rows[static_cast<size_t>(bh) * args.S + q]);
       uint16_t* optr = reinterpret_cast<uint16_t*>(args.o) + bh * args.o_head_stride +
                        out_row * args.o_row_stride;
+      float* optr32 = reinterpret_cast<float*>(args.o) + bh * args.o_head_stride + out_row * args.o_row_stride;
 #pragma unroll 1
       for (int g = 0; g < D / 32; ++g) {
         uint32_t o[32];
@@ -323,7 +325,17 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
 #pragma unroll
           for (int i = 0; i < 32; ++i) o[i] = 0u;
         }
-        if (row_ok) {
+        if (row_ok && args.out_f32) {
+#pragma unroll
+          for (int v = 0; v < 8; ++v) {
+            float4 w;
+            w.x = __uint_as_float(o[4 * v + 0]) * inv_l;
+            w.y = __uint_as_float(o[4 * v + 1]) * inv_l;
+            w.z = __uint_as_float(o[4 * v + 2]) * inv_l;
+            w.w = __uint_as_float(o[4 * v + 3]) * inv_l;
+            *reinterpret_cast<float4*>(optr32 + g * 32 + v * 4) = w;
+          }
+        } else if (row_ok) {
 #pragma unroll
           for (int v = 0; v < 4; ++v) {
             uint4 w;

@@ -1,0 +1,146 @@
+// identify_dynamic_map (svg/kmeans_utils.py:852-896) as one fused kernel: centroid scores, size-weighted
+// softmax, stable descending sort, top-p cut, scatter -- one CTA per (head, q-cluster).
+//
+// Every rounding the reference's torch ops perform on 16-bit tensors is reproduced:
+//   scores = round16(round16(qc . kc) / float(sqrt(D)))          (matmul then `/`, :877)
+//   prob   = round16(w * exp(s - max) / max(sum, 1e-12))         (weighted_softmax, :852-861, fp32 inside)
+//   sort descending; ties -> lower column first (the reference's torch.sort is unstable; we pin it)
+//   cums   = round16(fp32 running sum) per position              (torch.cumsum on a 16-bit tensor)
+//   keep[t] = t == 0 || !(cums[t-1] > round16(p)) || t < preserve   (:884-890; scalar compared in 16 bit)
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include "../../include/svgb200.h"
+#include "host_common.h"
+
+namespace svgb {
+
+template <bool BF16>
+__device__ __forceinline__ float h2f(uint16_t h) {
+  if constexpr (BF16) return __uint_as_float(static_cast<uint32_t>(h) << 16);
+  else return __half2float(__ushort_as_half(h));
+}
+template <bool BF16>
+__device__ __forceinline__ uint16_t f2h(float f) {
+  if constexpr (BF16) return __bfloat16_as_ushort(__float2bfloat16_rn(f));
+  else return __half_as_ushort(__float2half_rn(f));
+}
+
+__device__ __forceinline__ float block_reduce(float v, float* red, bool is_max) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int o = 16; o > 0; o >>= 1) {
+    const float other = __shfl_xor_sync(0xffffffffu, v, o);
+    v = is_max ? fmaxf(v, other) : v + other;
+  }
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float r = red[0];
+  for (int w = 1; w < nw; ++w) r = is_max ? fmaxf(r, red[w]) : r + red[w];
+  return r;
+}
+
+template <bool BF16>
+__global__ void __launch_bounds__(256)
+dynmap_kernel(const uint16_t* __restrict__ qc, const uint16_t* __restrict__ kc, const int* __restrict__ k_sizes,
+              int QC, int KC, int KCpad, int D, float top_p, int preserve, uint8_t* __restrict__ map) {
+  extern __shared__ uint32_t smem[];
+  uint32_t* keys = smem;                                  // KCpad
+  float* sc = reinterpret_cast<float*>(keys + KCpad);     // KCpad : scores, then weighted exps
+  float* qrow = sc + KCpad;                               // D
+  float* red = qrow + D;                                  // 32
+  uint8_t* keep = reinterpret_cast<uint8_t*>(red + 32);   // KCpad
+  const int i = blockIdx.x, bh = blockIdx.y;
+  const uint16_t* q = qc + (static_cast<size_t>(bh) * QC + i) * D;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) qrow[d] = h2f<BF16>(q[d]);
+  __syncthreads();
+  const float sqrt_d = static_cast<float>(sqrt(static_cast<double>(D)));
+  float mx = -INFINITY;
+  for (int j = threadIdx.x; j < KC; j += blockDim.x) {
+    const uint32_t* kr = reinterpret_cast<const uint32_t*>(kc + (static_cast<size_t>(bh) * KC + j) * D);
+    float acc = 0.f;
+    for (int d2 = 0; d2 < D / 2; ++d2) {
+      const uint32_t w = __ldg(kr + d2);
+      acc = fmaf(qrow[2 * d2], h2f<BF16>(static_cast<uint16_t>(w & 0xffff)), acc);
+      acc = fmaf(qrow[2 * d2 + 1], h2f<BF16>(static_cast<uint16_t>(w >> 16)), acc);
+    }
+    const float m = h2f<BF16>(f2h<BF16>(acc));
+    const float s = h2f<BF16>(f2h<BF16>(m / sqrt_d));
+    sc[j] = s;
+    mx = fmaxf(mx, s);
+  }
+  mx = block_reduce(mx, red, true);
+  float part = 0.f;
+  for (int j = threadIdx.x; j < KC; j += blockDim.x) {
+    const float e = static_cast<float>(k_sizes[static_cast<size_t>(bh) * KC + j]) * expf(sc[j] - mx);
+    sc[j] = e;
+    part += e;
+  }
+  const float denom = fmaxf(block_reduce(part, red, false), 1e-12f);
+  for (int j = threadIdx.x; j < KCpad; j += blockDim.x) {
+    uint32_t key = 0;
+    if (j < KC) {
+      const uint16_t pb = f2h<BF16>(sc[j] / denom);  // non-negative: bit pattern orders like the value
+      key = (static_cast<uint32_t>(pb) << 16) | static_cast<uint32_t>(0xFFFF - j);
+    }
+    keys[j] = key;
+  }
+  __syncthreads();
+  // bitonic sort, descending
+  for (int k = 2; k <= KCpad; k <<= 1) {
+    for (int jj = k >> 1; jj > 0; jj >>= 1) {
+      for (int t = threadIdx.x; t < KCpad; t += blockDim.x) {
+        const int p = t ^ jj;
+        if (p > t) {
+          const uint32_t a = keys[t], b = keys[p];
+          const bool desc = (t & k) == 0;
+          if (desc ? (a < b) : (a > b)) {
+            keys[t] = b;
+            keys[p] = a;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  if (threadIdx.x == 0) {
+    const float p16 = h2f<BF16>(f2h<BF16>(top_p));
+    float acc = 0.f, prev = 0.f;
+    for (int t = 0; t < KC; ++t) {
+      keep[t] = (t == 0) || !(prev > p16) || (t < preserve);
+      acc += h2f<BF16>(static_cast<uint16_t>(keys[t] >> 16));
+      prev = h2f<BF16>(f2h<BF16>(acc));
+    }
+  }
+  __syncthreads();
+  uint8_t* out = map + (static_cast<size_t>(bh) * QC + i) * KC;
+  for (int t = threadIdx.x; t < KC; t += blockDim.x) out[0xFFFF - (keys[t] & 0xFFFF)] = keep[t];
+}
+
+}  // namespace svgb
+
+using namespace svgb;
+
+extern "C" int svgb_dynamic_map(const void* qc, const void* kc, const int32_t* k_sizes, int BH, int QC,
+                                int KC, int D, int dtype, float top_p, int preserve, uint8_t* map,
+                                void* stream) {
+  SVGB_REQUIRE(qc && kc && k_sizes && map, "null pointer");
+  SVGB_REQUIRE(BH > 0 && QC > 0 && KC > 0 && KC <= 4096 && D > 0 && D % 2 == 0, "bad sizes (KC <= 4096)");
+  SVGB_REQUIRE(dtype == SVGB_BF16 || dtype == SVGB_F16, "dtype %d unsupported", dtype);
+  int KCpad = 2;
+  while (KCpad < KC) KCpad <<= 1;
+  const size_t smem = sizeof(uint32_t) * KCpad + sizeof(float) * (KCpad + D + 32) + KCpad;
+  dim3 grid(QC, BH);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == SVGB_BF16) {
+    SVGB_CUDA(cudaFuncSetAttribute(dynmap_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dynmap_kernel<true><<<grid, 256, smem, st>>>(static_cast<const uint16_t*>(qc), static_cast<const uint16_t*>(kc),
+                                                 k_sizes, QC, KC, KCpad, D, top_p, preserve, map);
+  } else {
+    SVGB_CUDA(cudaFuncSetAttribute(dynmap_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dynmap_kernel<false><<<grid, 256, smem, st>>>(static_cast<const uint16_t*>(qc), static_cast<const uint16_t*>(kc),
+                                                  k_sizes, QC, KC, KCpad, D, top_p, preserve, map);
+  }
+  SVGB_LAUNCH_OK();
+  return 0;
+}

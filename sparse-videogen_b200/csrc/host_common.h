@@ -48,6 +48,13 @@ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 int encode_tmap_hsd(CUtensorMap* map, const void* base, int dtype, int BH, int S, int D,
                     long long row_stride_elems, long long head_stride_elems, int box_rows = 128);
 
+struct AttnArgs;
+// attention launch with independent query / key-value geometry (attn_fwd.cu); used by svgb_attn_fwd
+// and by sample_mse's split-KV passes.
+int attn_fwd_impl(const void* q, int Sq, long long q_rs, long long q_hs, const void* k, const void* v, int Skv,
+                  long long kv_rs, long long kv_hs, int dtype, int BH, int D, const AttnArgs& a, int grid_x,
+                  cudaStream_t st);
+
 // stable counting-sort argsort (layout_ops.cu); `offs` (optional) receives the exclusive prefix of
 // counts per head; `skip_flag` (optional, device) turns the three kernels into no-ops when non-zero.
 int argsort_labels_impl(const int* labels, int BH, int S, int K, int* perm, int* counts, int* offs,

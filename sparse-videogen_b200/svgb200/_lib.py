@@ -46,13 +46,14 @@ _PROTOS = {
     "svgb_permute_gather": [_vp, _vp, _vp, _i, _i, _i, _vp],
     "svgb_permute_scatter": [_vp, _vp, _vp, _i, _i, _i, _vp],
     "svgb_head_placement": [C.POINTER(_vp), C.POINTER(_vp), _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
-    # TODO(pending) "svgb_kmeans_assign": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
-    # TODO(pending) "svgb_kmeans_update_bytes": [_i, _i, _i, _i, _psz],
-    # TODO(pending) "svgb_kmeans_update": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _sz, _vp],
-    # TODO(pending) "svgb_row_sqnorm": [_vp, _vp, _i, _i, _i, _i, _vp],
-    # TODO(pending) "svgb_dynamic_map": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _i, _vp, _vp],
-    # TODO(pending) "svgb_sample_mse_bytes": [_i, _i, _i, _i, _psz],
-    # TODO(pending) "svgb_sample_mse": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _sz, _vp],
+    "svgb_kmeans_bytes": [_i, _i, _i, _i, _psz],
+    "svgb_row_sqnorm": [_vp, _vp, _i, _i, _i, _i, _i, _vp],
+    "svgb_kmeans_assign": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _sz, _vp],
+    "svgb_kmeans_update": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _sz, _vp],
+    "svgb_kmeans_run": [_vp, _vp, _i, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _sz, _vp],
+    "svgb_dynamic_map": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _i, _vp, _vp],
+    "svgb_sample_mse_bytes": [_i, _i, _i, _i, _psz],
+    "svgb_sample_mse": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _sz, _vp],
     "svgb_selftest_tile": [_vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp],
 }
 

@@ -216,6 +216,106 @@ def head_placement(ins, outs, best_mask_idx, ctx, F, P, *, text_first=False, inv
     return outs
 
 
+# ----------------------------------------------------------------------------------------------
+# flash k-means
+# ----------------------------------------------------------------------------------------------
+def _km_ws(BH, N, K, D, device):
+    nbytes = C.c_size_t()
+    check(lib().svgb_kmeans_bytes(BH, N, K, D, C.byref(nbytes)), "svgb_kmeans_bytes")
+    return workspace(("km", BH, N, K, D), nbytes.value, device)
+
+
+def row_sqnorm(x, round_result=True):
+    """x [BH,N,D] 16-bit -> fp32 [BH,N]"""
+    _need_cuda(x)
+    BH, N, D = x.shape
+    xc = x.contiguous()
+    out = torch.empty(BH, N, dtype=torch.float32, device=x.device)
+    check(lib().svgb_row_sqnorm(xc.data_ptr(), out.data_ptr(), BH, N, D, _dt(x), 1 if round_result else 0,
+                                _stream(x)), "svgb_row_sqnorm")
+    _bump()
+    return out
+
+
+def kmeans_assign(x, c, x_sq):
+    _need_cuda(x, c, x_sq)
+    BH, N, D = x.shape
+    K = c.shape[1]
+    xc, cc = x.contiguous(), c.contiguous()
+    ws = _km_ws(BH, N, K, D, x.device)
+    labels = torch.empty(BH, N, dtype=torch.int32, device=x.device)
+    check(lib().svgb_kmeans_assign(xc.data_ptr(), cc.data_ptr(), x_sq.contiguous().data_ptr(), labels.data_ptr(),
+                                   BH, N, K, D, _dt(x), ws.data_ptr(), ws.numel(), _stream(x)),
+          "svgb_kmeans_assign")
+    _bump(2)
+    return labels
+
+
+def kmeans_update(x, labels, c_old):
+    _need_cuda(x, labels, c_old)
+    BH, N, D = x.shape
+    K = c_old.shape[1]
+    ws = _km_ws(BH, N, K, D, x.device)
+    c_new = torch.empty_like(c_old.contiguous())
+    counts = torch.empty(BH, K, dtype=torch.int32, device=x.device)
+    shift = torch.zeros(1, dtype=torch.float32, device=x.device)
+    check(lib().svgb_kmeans_update(x.contiguous().data_ptr(), labels.to(torch.int32).contiguous().data_ptr(),
+                                   c_old.contiguous().data_ptr(), c_new.data_ptr(), counts.data_ptr(),
+                                   shift.data_ptr(), BH, N, K, D, _dt(x), ws.data_ptr(), ws.numel(), _stream(x)),
+          "svgb_kmeans_update")
+    _bump(5)
+    return c_new, counts, shift
+
+
+def kmeans_run(x, init_centroids, max_iters, tol=1e-4):
+    """Whole Lloyd loop on the device (no host sync).  Returns labels int32 [BH,N], centroids [BH,K,D],
+    counts int32 [BH,K], n_iter int32[1] (device)."""
+    _need_cuda(x, init_centroids)
+    BH, N, D = x.shape
+    K = init_centroids.shape[1]
+    ws = _km_ws(BH, N, K, D, x.device)
+    labels = torch.empty(BH, N, dtype=torch.int32, device=x.device)
+    cents = torch.empty(BH, K, D, dtype=x.dtype, device=x.device)
+    counts = torch.empty(BH, K, dtype=torch.int32, device=x.device)
+    n_iter = torch.zeros(1, dtype=torch.int32, device=x.device)
+    check(lib().svgb_kmeans_run(x.contiguous().data_ptr(), init_centroids.contiguous().data_ptr(), BH, N, K, D,
+                                _dt(x), int(max_iters), float(tol), labels.data_ptr(), cents.data_ptr(),
+                                counts.data_ptr(), n_iter.data_ptr(), ws.data_ptr(), ws.numel(), _stream(x)),
+          "svgb_kmeans_run")
+    _bump(3 + 7 * int(max_iters))
+    return labels, cents, counts, n_iter
+
+
+def dynamic_map(qc, kc, k_sizes, top_p, preserve):
+    """qc [BH,QC,D], kc [BH,KC,D] 16-bit, k_sizes int [BH,KC] -> bool [BH,QC,KC]"""
+    _need_cuda(qc, kc, k_sizes)
+    BH, QC, D = qc.shape
+    KC = kc.shape[1]
+    out = torch.empty(BH, QC, KC, dtype=torch.uint8, device=qc.device)
+    check(lib().svgb_dynamic_map(qc.contiguous().data_ptr(), kc.contiguous().data_ptr(),
+                                 k_sizes.to(torch.int32).contiguous().data_ptr(), BH, QC, KC, D, _dt(qc),
+                                 float(top_p), int(preserve), out.data_ptr(), _stream(qc)), "svgb_dynamic_map")
+    _bump()
+    return out.view(torch.bool)
+
+
+def sample_mse(q, k, v, rows, layout, ctx, F, P):
+    """q,k,v [BH,S,D]; rows int [n] (<=128) -> fp32 [2, BH] (0 = spatial mask, 1 = temporal mask)"""
+    _need_cuda(q, k, v, rows)
+    BH, S, D = q.shape
+    n = rows.numel()
+    nbytes = C.c_size_t()
+    check(lib().svgb_sample_mse_bytes(BH, S, D, n, C.byref(nbytes)), "svgb_sample_mse_bytes")
+    ws = workspace(("smse", BH, S, D), nbytes.value, q.device)
+    out = torch.empty(2, BH, dtype=torch.float32, device=q.device)
+    r = rows.to(torch.int32).contiguous()
+    check(lib().svgb_sample_mse(q.contiguous().data_ptr(), k.contiguous().data_ptr(), v.contiguous().data_ptr(),
+                                r.data_ptr(), n, BH, S, D, _dt(q), int(layout), ctx, F, P, out.data_ptr(),
+                                ws.data_ptr(), ws.numel(), _stream(q)), "svgb_sample_mse")
+    _bump(6)
+    return out
+
+
 def selftest_tile(q, k, v, p_scale=0.0625):
     """q,k,v: [128, D] -> (S fp32 [128,128], O fp32 [128,D])"""
     _need_cuda(q, k, v)

@@ -1,0 +1,236 @@
+"""Shared host logic of the SVG1 / SVG2 attention cores (what attention_core_logic does between the QKV
+projection and the output projection in svg/models/<m>/attention.py)."""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+
+from .. import core
+from ..kmeans_utils import batch_kmeans_Euclid
+
+
+def sparsity_to_width(sparsity, context_length, num_frame, frame_size):
+    """svg/models/hyvideo/utils.py:142-151 (identical in wan / cog)."""
+    seq_len = context_length + num_frame * frame_size
+    total_elements = seq_len ** 2
+    sparsity = (sparsity * total_elements - 2 * seq_len * context_length) / total_elements
+    width = seq_len * (1 - math.sqrt(1 - sparsity))
+    return width / frame_size
+
+
+@dataclass
+class BandMask:
+    """What the reference's torch BlockMask is to flex_attention: the compiled executed mask.
+    Built once (prepare_flexattention) and shared by every head / layer / step."""
+    plan: core.AttnPlan
+    mode: int
+    m0: int
+    m1: int
+    m2: int
+    seq_len: int
+
+
+def sparse_flex_attention(query, key, value, block_mask: BandMask):
+    """hyvideo/attention.py:401-403: flex_attention(q, k, v, block_mask=...)  [cfg,H,S,D]."""
+    return core.attn_fwd(query, key, value, block_mask.plan)
+
+
+def dense_attention(query, key, value, seg_lens=None):
+    """Dense fall-back (b11).  seg_lens: optional list of segment lengths that only attend inside
+    themselves (HunyuanVideo's padded-prompt varlen split, hyvideo/attention.py:308-316,807-875)."""
+    cfg, H, S, D = query.shape
+    dev = query.device
+    segs = [S] if seg_lens is None else [int(x) for x in seg_lens]
+    n = len(segs)
+    bm = torch.eye(n, dtype=torch.bool, device=dev).expand(cfg * H, n, n).contiguous()
+    sz = torch.tensor(segs, dtype=torch.int32, device=dev).expand(cfg * H, n).contiguous()
+    plan = core.plan_varblock(bm, sz, sz, S)
+    return core.attn_fwd(query, key, value, plan)
+
+
+class KMeansState:
+    """Centroids persist across diffusion steps and warm-start the next call (hyvideo/attention.py:
+    566-626 keeps them in class-level dicts keyed by layer; wan keeps them per processor instance)."""
+
+    def __init__(self):
+        self.q_centroids = {}
+        self.k_centroids = {}
+
+    def cluster(self, key, query, kmat, num_q, num_k, iters_init, iters_step):
+        """query/kmat: [BH, N, D].  Returns (qlabels, qcent, qsizes, klabels, kcent, ksizes)."""
+        if key not in self.q_centroids:
+            ql, qc, qs, _ = batch_kmeans_Euclid(query, num_q, max_iters=iters_init)
+            kl, kc, ks, _ = batch_kmeans_Euclid(kmat, num_k, max_iters=iters_init)
+        else:
+            ql, qc, qs, _ = batch_kmeans_Euclid(query, num_q, max_iters=iters_step, init_centroids=self.q_centroids[key])
+            kl, kc, ks, _ = batch_kmeans_Euclid(kmat, num_k, max_iters=iters_step, init_centroids=self.k_centroids[key])
+        self.q_centroids[key] = qc
+        self.k_centroids[key] = kc
+        return ql, qc, qs, kl, kc, ks
+
+
+class SVG1Core:
+    """Sparse VideoGen v1 attention core: online profiling -> head placement -> one band mask -> inverse
+    placement (svg/models/hyvideo/attention.py:473-524; wan :284-328; cosmos :200-238; cog :164-196).
+
+    Subclasses fix the text layout (`text_first`, `smse_layout`) and build `block_mask`."""
+
+    text_first = False
+    smse_layout = 0  # svgb_sample_mse layout id (0 = HY text-last band 1.5*P, 1 = WAN sink band 2*P)
+
+    def __init__(self, context_length, num_frame, frame_size, num_sampled_rows=64, sample_mse_max_row=10000,
+                 first_layers_fp=0, first_times_fp=0, layer_idx=0):
+        self.context_length, self.num_frame, self.frame_size = context_length, num_frame, frame_size
+        self.num_sampled_rows, self.sample_mse_max_row = num_sampled_rows, sample_mse_max_row
+        self.first_layers_fp, self.first_times_fp, self.layer_idx = first_layers_fp, first_times_fp, layer_idx
+        self.block_mask: Optional[BandMask] = None
+
+    # -- reference method names ---------------------------------------------------------------------
+    def sample_mse(self, query, key, value, sampled_rows=None):
+        """hyvideo/attention.py:375-399 -> [2, cfg, H] in query.dtype (0 = spatial, 1 = temporal).
+        `sampled_rows` defaults to torch.randint on the CPU generator exactly like the reference (:381)."""
+        cfg, H, S, D = query.shape
+        n = min(self.num_sampled_rows, S)
+        if sampled_rows is None:
+            sampled_rows = torch.randint(low=0, high=self.sample_mse_max_row, size=(n,))
+        rows = sampled_rows.to(query.device, non_blocking=True)
+        mse = core.sample_mse(query.view(cfg * H, S, D), key.view(cfg * H, S, D), value.view(cfg * H, S, D), rows,
+                              self.smse_layout, self.context_length, self.num_frame, self.frame_size)
+        return mse.view(2, cfg, H).to(query.dtype)
+
+    def sparse_flex_attention(self, query, key, value, block_mask):
+        return sparse_flex_attention(query, key, value, block_mask)
+
+    def fast_sparse_head_placement(self, query, key, value, query_out, key_out, value_out, best_mask_idx,
+                                   context_length, num_frame, frame_size):
+        core.head_placement([query, key, value], [query_out, key_out, value_out], best_mask_idx, context_length,
+                            num_frame, frame_size, text_first=self.text_first)
+        return query_out, key_out, value_out
+
+    def fast_hidden_states_placement(self, hidden_states, output_hidden_states, best_mask_idx, context_length,
+                                     num_frame, frame_size):
+        core.head_placement([hidden_states], [output_hidden_states], best_mask_idx, context_length, num_frame,
+                            frame_size, text_first=self.text_first, inverse=True)
+
+    # -- the sparse branch ---------------------------------------------------------------------------
+    def sparse_core(self, query, key, value, sampled_rows=None, attn_events=None):
+        sampled_mses = self.sample_mse(query, key, value, sampled_rows)
+        best_mask_idx = torch.argmin(sampled_mses, dim=0)  # ties -> 0 (spatial), like the reference (:508)
+        q_out, k_out, v_out = torch.empty_like(query), torch.empty_like(key), torch.empty_like(value)
+        self.fast_sparse_head_placement(query, key, value, q_out, k_out, v_out, best_mask_idx, self.context_length,
+                                        self.num_frame, self.frame_size)
+        if attn_events is not None:
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+        hidden = self.sparse_flex_attention(q_out, k_out, v_out, self.block_mask)
+        if attn_events is not None:
+            b.record()
+            attn_events.append((a, b))
+        out = torch.empty_like(query)
+        self.fast_hidden_states_placement(hidden, out, best_mask_idx, self.context_length, self.num_frame,
+                                          self.frame_size)
+        return out
+
+    def dense_core(self, query, key, value, cu_max_seqlens=None):
+        seg = None
+        if cu_max_seqlens is not None:
+            cu = cu_max_seqlens[0]
+            seg = (cu[1:] - cu[:-1]).tolist()
+            seg = [s for s in seg if s > 0]
+        return dense_attention(query, key, value, seg)
+
+    def attention_core_logic(self, query, key, value, timestep, layer_idx=None, cu_max_seqlens=None):
+        cfg, H, S, D = query.shape
+        assert S == self.context_length + self.num_frame * self.frame_size, (
+            f"Query Shape: {S} is not equivalent to {self.context_length} + {self.num_frame} * {self.frame_size}")
+        full = self.layer_idx < self.first_layers_fp or bool(timestep[0] > self.first_times_fp)
+        if full:
+            return self.dense_core(query, key, value, cu_max_seqlens)
+        return self.sparse_core(query, key, value)
+
+
+class SAPCore:
+    """Sparse VideoGen v2 (semantic-aware permutation) attention core
+    (svg/models/hyvideo/attention.py:555-804; wan :375-559; cosmos :290-469).
+
+    k-means on Q and K -> centroid top-p dynamic map -> permute Q,K,V by cluster -> variable-block sparse
+    attention -> inverse permutation.  Here the inverse permutation is fused into the attention epilogue
+    (o_rows) and the text tokens ride the same gather (no write-back copies)."""
+
+    def __init__(self, context_length, num_frame, frame_size, num_q_centroids, num_k_centroids, top_p_kmeans,
+                 min_kc_ratio, kmeans_iter_init, kmeans_iter_step, prompt_length=0, zero_step_kmeans_init=False,
+                 first_layers_fp=0, first_times_fp=0, layer_idx=0, state: Optional[KMeansState] = None):
+        self.context_length, self.num_frame, self.frame_size = context_length, num_frame, frame_size
+        self.prompt_length = prompt_length
+        self.num_q_centroids, self.num_k_centroids = num_q_centroids, num_k_centroids
+        self.top_p_kmeans, self.min_kc_ratio = top_p_kmeans, min_kc_ratio
+        self.kmeans_iter_init, self.kmeans_iter_step = kmeans_iter_init, kmeans_iter_step
+        self.zero_step_kmeans_init = zero_step_kmeans_init
+        self.first_layers_fp, self.first_times_fp, self.layer_idx = first_layers_fp, first_times_fp, layer_idx
+        self.state = state if state is not None else KMeansState()
+        self.last = {}
+
+    def kmeans_clustering(self, query_video, key_video, layer_idx):
+        BH, N, D = query_video.shape[0] * query_video.shape[1], query_video.shape[2], query_video.shape[3]
+        return self.state.cluster(layer_idx, query_video.reshape(BH, N, D), key_video.reshape(BH, N, D),
+                                  self.num_q_centroids, self.num_k_centroids, self.kmeans_iter_init,
+                                  self.kmeans_iter_step)
+
+    def sparse_core(self, query, key, value, layer_idx=None):
+        from ..kmeans_utils import identify_dynamic_map
+
+        cfg, H, S, D = query.shape
+        assert cfg == 1, "Batch size must be 1 for kmeans block sparse attention"
+        layer_idx = self.layer_idx if layer_idx is None else layer_idx
+        ctx, V = self.context_length, self.num_frame * self.frame_size
+        dev = query.device
+        qv = query[:, :, :V].contiguous() if ctx else query
+        kv = key[:, :, :V].contiguous() if ctx else key
+        ql, qc, qs, kl, kc, ks = self.kmeans_clustering(qv, kv, layer_idx)
+        QC, KC = self.num_q_centroids, self.num_k_centroids
+        dyn = identify_dynamic_map(qc.view(cfg, H, QC, D), kc.view(cfg, H, KC, D), qs.view(cfg, H, QC),
+                                   ks.view(cfg, H, KC), self.top_p_kmeans, self.min_kc_ratio).view(H, QC, KC)
+        q_perm, _ = core.argsort_labels(ql.view(H, V), QC)
+        k_perm, _ = core.argsort_labels(kl.view(H, V), KC)
+        row_sz, col_sz = qs.view(H, QC), ks.view(H, KC)
+        if ctx:
+            # HunyuanVideo: prompt block <-> everything but the padding, padding <-> itself
+            # (dynamic_map_post_processing, hyvideo/attention.py:657-702)
+            unprompt = ctx - self.prompt_length
+            tail = torch.arange(V, S, device=dev, dtype=torch.int32).expand(H, ctx)
+            q_perm = torch.cat([q_perm, tail], dim=1)
+            k_perm = torch.cat([k_perm, tail], dim=1)
+            dyn = torch.nn.functional.pad(dyn, (0, 2, 0, 2), value=False)
+            dyn[:, -2, :-1] = True
+            dyn[:, :-1, -2] = True
+            dyn[:, -1, -1] = True
+            extra = torch.tensor([self.prompt_length, unprompt], dtype=torch.int32, device=dev).expand(H, 2)
+            row_sz = torch.cat([row_sz, extra], dim=1)
+            col_sz = torch.cat([col_sz, extra], dim=1)
+        qp = core.permute_gather(query, q_perm)
+        kp = core.permute_gather(key, k_perm)
+        vp = core.permute_gather(value, k_perm)
+        plan = core.plan_varblock(dyn, row_sz, col_sz, S)
+        out = core.attn_fwd(qp, kp, vp, plan, o_rows=q_perm)  # inverse permutation fused into the store
+        self.last = {"dynamic_map": dyn, "q_sizes": row_sz, "k_sizes": col_sz, "q_sorted_indices": q_perm,
+                     "k_sorted_indices": k_perm}
+        return out
+
+    def attention_core_logic(self, query, key, value, timestep, layer_idx=None, cu_max_seqlens=None):
+        cfg, H, S, D = query.shape
+        layer_idx = self.layer_idx if layer_idx is None else layer_idx
+        assert S == self.context_length + self.num_frame * self.frame_size
+        full = self.layer_idx < self.first_layers_fp or bool(timestep[0] > self.first_times_fp)
+        if full:
+            if self.zero_step_kmeans_init:
+                V = self.num_frame * self.frame_size
+                self.kmeans_clustering(query[:, :, :V].contiguous(), key[:, :, :V].contiguous(), layer_idx)
+            seg = None
+            if cu_max_seqlens is not None:
+                cu = cu_max_seqlens[0]
+                seg = [s for s in (cu[1:] - cu[:-1]).tolist() if s > 0]
+            return dense_attention(query, key, value, seg)
+        return self.sparse_core(query, key, value, layer_idx)
