@@ -45,19 +45,20 @@ enum MaskMode : int {
 };
 
 __host__ __device__ inline bool mask_allowed(int mode, int q, int kv, int m0, int m1, int m2) {
+  // reference semantics, written branch-free (bitwise) so warps do not diverge on it
   int d = q - kv;
   d = d < 0 ? -d : d;
   switch (mode) {
     case MASK_HY: {
-      bool real = (q < m1) && (kv < m1);
-      bool fake = (q >= m1) && (kv >= m1);
-      bool vid = (d < m2) || (kv >= m0) || (q >= m0);
-      return (real && vid) || fake;
+      const bool real = (q < m1) & (kv < m1);
+      const bool fake = (q >= m1) & (kv >= m1);
+      const bool vid = (d < m2) | (kv >= m0) | (q >= m0);
+      return (real & vid) | fake;
     }
     case MASK_WAN:
-      return (kv < m0) || (d <= m2);
+      return (kv < m0) | (d <= m2);
     case MASK_COG:
-      return (kv < m0) || (q < m1) || (d < m2);
+      return (kv < m0) | (q < m1) | (d < m2);
     case MASK_PROF_HY_S:
     case MASK_PROF_HY_T:
     case MASK_PROF_WAN_S:
@@ -70,12 +71,61 @@ __host__ __device__ inline bool mask_allowed(int mode, int q, int kv, int m0, in
       const int ki = temporal ? (kv % P) * F + kv / P : kv;
       int bd = qi / 128 - ki / 128;
       bd = bd < 0 ? -bd : bd;
-      return (bd < m2) || (!hy && ki < P);
+      return (bd < m2) | (!hy & (ki < P));
     }
     default:
       return true;
   }
 }
+
+// Device-side evaluator of the same predicate for 32 consecutive key columns of one query row:
+// row-constant terms are hoisted, the token-major index of the profiling masks is advanced
+// incrementally (one division per 32 columns instead of two per element), and the result is a bitmask.
+struct MaskRow {
+  int mode, q, m0, m1, m2;
+  int qi_blk;     // profiling masks: 128-token block of the (possibly token-major) query index
+  bool q_text;    // profiling masks: query row is a text row
+  __device__ __forceinline__ void init(int mode_, int q_, int m0_, int m1_, int m2_) {
+    mode = mode_; q = q_; m0 = m0_; m1 = m1_; m2 = m2_;
+    qi_blk = 0; q_text = false;
+    if (mode >= MASK_PROF_HY_S) {
+      const int F = m0, P = m1, V = F * P;
+      const bool temporal = (mode == MASK_PROF_HY_T) | (mode == MASK_PROF_WAN_T);
+      q_text = q >= V;
+      const int qq = q_text ? 0 : q;
+      qi_blk = (temporal ? (qq % P) * F + qq / P : qq) >> 7;
+    }
+  }
+  // bit i set <=> (q, kv0 + i) allowed
+  __device__ __forceinline__ uint32_t bits32(int kv0) const {
+    uint32_t out = 0;
+    if (mode >= MASK_PROF_HY_S) {
+      const int F = m0, P = m1, V = F * P;
+      const bool hy = mode <= MASK_PROF_HY_T;
+      const bool temporal = (mode == MASK_PROF_HY_T) | (mode == MASK_PROF_WAN_T);
+      const int kvc = kv0 < V ? kv0 : 0;
+      int f = kvc / P, p = kvc - f * P;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const int kv = kv0 + i;
+        const int ki = temporal ? p * F + f : kv;
+        int bd = qi_blk - (ki >> 7);
+        bd = bd < 0 ? -bd : bd;
+        const bool text = q_text | (kv >= V);
+        const bool a = text ? hy : ((bd < m2) | (!hy & (ki < P)));
+        out |= (a ? 1u : 0u) << i;
+        ++p;
+        const bool wrap = p == P;
+        p = wrap ? 0 : p;
+        f += wrap ? 1 : 0;
+      }
+      return out;
+    }
+#pragma unroll
+    for (int i = 0; i < 32; ++i) out |= (mask_allowed(mode, q, kv0 + i, m0, m1, m2) ? 1u : 0u) << i;
+    return out;
+  }
+};
 
 struct AttnArgs {
   const int4* items;

@@ -88,15 +88,30 @@ __global__ void plan_varblock_kernel(const uint8_t* __restrict__ map, const int*
 }
 
 // =============================================================================================
-// Plan: element-exact band masks (SVG1).  One CTA per 256-row item; thread = query row; for every
+// Plan: element-exact band masks (SVG1).  One CTA per work item; thread = query row; for every
 // 128-column chunk the block votes any/all over the item's rows.  Exact by construction.
+// Items never straddle a row-region boundary of the mask (video | prompt | padding for HunyuanVideo,
+// text | video for CogVideoX), so text rows -- which see every column -- do not drag 256-row items of
+// video rows onto the per-element path; the heavy text items are issued first (LPT).
 // =============================================================================================
-__global__ void plan_band_kernel(int mode, int m0, int m1, int m2, int S, int n_chunks_total,
+struct BandSegs {
+  int n;             // number of row segments
+  int bound[6];      // bound[s] .. bound[s+1]
+  int item_base[6];  // first item index of segment s (launch order)
+  int item_cnt[6];
+};
+
+__global__ void plan_band_kernel(int mode, int m0, int m1, int m2, int S, int n_chunks_total, BandSegs segs,
                                  int* __restrict__ counts, int4* __restrict__ items,
                                  int2* __restrict__ chunks) {
   const int item = blockIdx.x;
-  const int q = item * kItemRows + threadIdx.x;
-  const bool row_live = q < S;
+  int seg = 0;
+  for (int s = 0; s < segs.n; ++s)
+    if (item >= segs.item_base[s] && item < segs.item_base[s] + segs.item_cnt[s]) seg = s;
+  const int q_row0 = segs.bound[seg] + (item - segs.item_base[seg]) * kItemRows;
+  const int nrows = min(kItemRows, segs.bound[seg + 1] - q_row0);
+  const int q = q_row0 + threadIdx.x;
+  const bool row_live = static_cast<int>(threadIdx.x) < nrows;
   int2* out = chunks + static_cast<size_t>(item) * n_chunks_total;
   int n = 0;
   for (int c = 0; c < n_chunks_total; ++c) {
@@ -118,10 +133,47 @@ __global__ void plan_band_kernel(int mode, int m0, int m1, int m2, int S, int n_
     }
   }
   if (threadIdx.x == 0) {
-    items[item] = make_int4(item * kItemRows, min(kItemRows, S - item * kItemRows),
-                            static_cast<int>(static_cast<size_t>(item) * n_chunks_total), n);
+    items[item] = make_int4(q_row0, nrows, static_cast<int>(static_cast<size_t>(item) * n_chunks_total), n);
     if (item == 0) counts[0] = gridDim.x;
   }
+}
+
+// row-region boundaries of each mask family, and the launch order of the segments
+static BandSegs band_segments(int mode, int m0, int m1, int S) {
+  int cuts[4], nc = 0;
+  auto add = [&](int c) {
+    if (c > 0 && c < S && (nc == 0 || cuts[nc - 1] < c)) cuts[nc++] = c;
+  };
+  if (mode == MASK_HY) {
+    add(m0);  // end of video
+    add(m1);  // end of real prompt
+  } else if (mode == MASK_COG) {
+    add(m1);  // end of text prefix
+  }
+  BandSegs sg{};
+  sg.n = nc + 1;
+  sg.bound[0] = 0;
+  for (int i = 0; i < nc; ++i) sg.bound[i + 1] = cuts[i];
+  sg.bound[sg.n] = S;
+  for (int s = 0; s < sg.n; ++s) sg.item_cnt[s] = (sg.bound[s + 1] - sg.bound[s] + kItemRows - 1) / kItemRows;
+  int base = 0;
+  if (mode == MASK_HY) {  // text segments (heavy: they see every column) first
+    for (int s = sg.n - 1; s >= 0; --s) {
+      sg.item_base[s] = base;
+      base += sg.item_cnt[s];
+    }
+  } else {
+    for (int s = 0; s < sg.n; ++s) {
+      sg.item_base[s] = base;
+      base += sg.item_cnt[s];
+    }
+  }
+  return sg;
+}
+static int band_total_items(const BandSegs& sg) {
+  int t = 0;
+  for (int s = 0; s < sg.n; ++s) t += sg.item_cnt[s];
+  return t;
 }
 
 // =============================================================================================
@@ -343,7 +395,7 @@ int svgb_attn_plan_varblock(const uint8_t* map, const int32_t* row_sz, const int
 
 int svgb_attn_plan_band_bytes(int S, size_t* bytes) {
   SVGB_REQUIRE(S > 0 && bytes, "bad arguments");
-  const size_t n_items = (S + kItemRows - 1) / kItemRows;
+  const size_t n_items = (S + kItemRows - 1) / kItemRows + 4;  // + one partial item per extra row segment
   const size_t n_chunks = (S + kChunkCols - 1) / kChunkCols;
   *bytes = 256 + align_up(sizeof(int4) * n_items, 256) + align_up(sizeof(int2) * n_items * n_chunks, 256);
   return 0;
@@ -356,9 +408,12 @@ int svgb_attn_plan_band(int mask_mode, int m0, int m1, int m2, int BH, int S, vo
   SVGB_REQUIRE(plan_ws && plan, "null pointer");
   SVGB_REQUIRE(ws_bytes >= need, "plan workspace too small: %zu < %zu", ws_bytes, need);
   SVGB_REQUIRE(mask_mode >= MASK_NONE && mask_mode <= MASK_COG, "unknown mask mode %d", mask_mode);
-  const int n_items = (S + kItemRows - 1) / kItemRows;
+  const BandSegs sg = band_segments(mask_mode, m0, m1, S);
+  const int n_items = band_total_items(sg);
+  const int n_items_cap = (S + kItemRows - 1) / kItemRows + 4;
   const int n_chunks = (S + kChunkCols - 1) / kChunkCols;
-  SVGB_REQUIRE(static_cast<size_t>(n_items) * n_chunks < (1ull << 31), "plan too large");
+  SVGB_REQUIRE(n_items <= n_items_cap, "internal: item count");
+  SVGB_REQUIRE(static_cast<size_t>(n_items_cap) * n_chunks < (1ull << 31), "plan too large");
   plan->kind = 2;
   plan->BH = BH;
   plan->S = S;
@@ -371,11 +426,11 @@ int svgb_attn_plan_band(int mask_mode, int m0, int m1, int m2, int BH, int S, vo
   plan->m2 = m2;
   plan->counts_off = 0;
   plan->items_off = 256;
-  plan->chunks_off = 256 + align_up(sizeof(int4) * n_items, 256);
+  plan->chunks_off = 256 + align_up(sizeof(int4) * n_items_cap, 256);
   plan->bytes = need;
   char* ws = static_cast<char*>(plan_ws);
   plan_band_kernel<<<n_items, kItemRows, 0, static_cast<cudaStream_t>(stream)>>>(
-      mask_mode, m0, m1, m2, S, n_chunks, reinterpret_cast<int*>(ws + plan->counts_off),
+      mask_mode, m0, m1, m2, S, n_chunks, sg, reinterpret_cast<int*>(ws + plan->counts_off),
       reinterpret_cast<int4*>(ws + plan->items_off), reinterpret_cast<int2*>(ws + plan->chunks_off));
   SVGB_LAUNCH_OK();
   return 0;

@@ -226,6 +226,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
       float m_used = -INFINITY;  // reference max the stored P / O are scaled against
       float l_run = 0.f;
       int2 ch = nchunks > 0 ? __ldg(&chunks[0]) : make_int2(0, 0);
+      MaskRow mrow;
+      mrow.init(mode, qm, m0, m1, m2);
 
       for (int j = 0; j < nchunks; ++j) {
         const int kv0 = ch.x;
@@ -239,27 +241,27 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
         tc_fence_after();
 
         uint32_t r[32];
-        auto load_group = [&](int g) {
-          tmem_ld32(s_addr + g * 32, r);
-          tc_wait_ld();
-          if (g * 32 + 32 > valid) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (g * 32 + i >= valid) r[i] = 0xff800000u;  // -inf
-          }
-          if (elem) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (!mask_allowed(mode, qm, kv0 + g * 32 + i, m0, m1, m2)) r[i] = 0xff800000u;
-          }
-        };
-
-        // pass 1: row max of the raw scores
+        uint32_t mbits[4];  // per 32-column group: which columns this row may attend (tail + element mask)
+        // pass 1: row max of the raw scores (the mask bits are computed here once and reused in pass 2)
         float mx = -INFINITY;
-        for (int g = 0; g < ngroups; ++g) {
-          load_group(g);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
+        for (int g = 0; g < 4; ++g) {
+          if (g >= ngroups) break;
+          tmem_ld32(s_addr + g * 32, r);
+          uint32_t bits = 0xffffffffu;
+          const int left = valid - g * 32;  // columns of this group that exist
+          if (left < 32) bits = (1u << left) - 1u;
+          if (elem) bits &= mrow.bits32(kv0 + g * 32);
+          mbits[g] = bits;
+          tc_wait_ld();
+          if (elem || left < 32) {  // warp-uniform
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              mx = fmaxf(mx, (bits >> i) & 1u ? __uint_as_float(r[i]) : -INFINITY);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
+          }
         }
         const float m_new = fmaxf(m_used, mx);
         // lazy rescale: keep the stale reference max unless it grew by more than tau (log2 units)
@@ -285,13 +287,22 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
 
         // pass 2: P = exp2(S*c - m*c) -> 16-bit, packed two per TMEM column over the S tile
         float rs = 0.f;
-        for (int g = 0; g < ngroups; ++g) {
-          load_group(g);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          if (g >= ngroups) break;
+          tmem_ld32(s_addr + g * 32, r);
+          tc_wait_ld();
+          const uint32_t bits = mbits[g];
+          const bool masked = elem || (valid - g * 32) < 32;  // warp-uniform
           uint32_t pk[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            const float p0 = ex2_approx(fmaf(__uint_as_float(r[2 * i]), c, -mc));
-            const float p1 = ex2_approx(fmaf(__uint_as_float(r[2 * i + 1]), c, -mc));
+            float p0 = ex2_approx(fmaf(__uint_as_float(r[2 * i]), c, -mc));
+            float p1 = ex2_approx(fmaf(__uint_as_float(r[2 * i + 1]), c, -mc));
+            if (masked) {
+              p0 = (bits >> (2 * i)) & 1u ? p0 : 0.f;
+              p1 = (bits >> (2 * i + 1)) & 1u ? p1 : 0.f;
+            }
             rs += p0 + p1;
             pk[i] = pack2<BF16>(p0, p1);
           }

@@ -107,7 +107,7 @@ struct SmseLayout {
 static SmseLayout smse_layout(int BH, int S, int D) {
   SmseLayout L;
   L.n_chunks = (S + kChunkCols - 1) / kChunkCols;
-  L.nsplit = (148 + BH - 1) / BH;
+  L.nsplit = 148 / BH;  // one wave: BH * nsplit <= number of SMs
   if (L.nsplit > L.n_chunks) L.nsplit = L.n_chunks;
   if (L.nsplit < 1) L.nsplit = 1;
   size_t o = 0;

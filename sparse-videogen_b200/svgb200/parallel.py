@@ -1,0 +1,76 @@
+"""Head-parallel execution over the GPUs of one NVSwitch box.
+
+Every op on the hot path is independent per (batch, head), so the only exchange step is the all-gather
+of the attention output, and only when the consumer needs all heads.  Rank r owns heads h with
+h % world == r (interleaved): the heads gathered for local head index i are then the contiguous slice
+[i*world, (i+1)*world) of the full [H, S, D] output, so each per-head all-gather writes straight into
+the final tensor (ncclAllGather, no staging copy) and can be issued on a side stream as soon as that
+head's attention finishes — the transfer of head i overlaps the attention of head i+1.
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional
+
+import torch
+import torch.distributed as dist
+
+
+def owned_heads(num_heads: int, world: int, rank: int):
+    """heads owned by `rank` (interleaved assignment)."""
+    assert num_heads % world == 0, "number of heads must divide across ranks"
+    return list(range(rank, num_heads, world))
+
+
+def shard_heads(t: torch.Tensor, world: int, rank: int) -> torch.Tensor:
+    """[cfg, H, S, D] -> contiguous [cfg, H/world, S, D] slice owned by `rank`."""
+    return t[:, rank::world].contiguous()
+
+
+class HeadParallel:
+    def __init__(self, group: Optional[dist.ProcessGroup] = None):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self._comm_stream = None
+
+    def local_heads(self, num_heads: int):
+        return owned_heads(num_heads, self.world, self.rank)
+
+    def gather_heads(self, o_local: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """o_local [1, Hl, S, D] -> [1, Hl*world, S, D] (blocking w.r.t. the current stream)."""
+        cfg, Hl, S, D = o_local.shape
+        assert cfg == 1
+        if self.world == 1:
+            return o_local
+        if out is None:
+            out = torch.empty(1, Hl * self.world, S, D, dtype=o_local.dtype, device=o_local.device)
+        for i in range(Hl):
+            dist.all_gather_into_tensor(out[0, i * self.world:(i + 1) * self.world], o_local[0, i:i + 1].contiguous(),
+                                        group=self.group)
+        return out
+
+    def run_overlapped(self, per_head_fn: Callable[[int], torch.Tensor], num_local_heads: int, S: int, D: int,
+                       dtype, device, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """per_head_fn(i) computes local head i ([S, D] or [1,1,S,D]) on the current stream; its all-gather
+        is issued on a side stream so it overlaps the next head's compute (CUDA / NCCL only)."""
+        H = num_local_heads * self.world
+        if out is None:
+            out = torch.empty(1, H, S, D, dtype=dtype, device=device)
+        if self.world == 1:
+            for i in range(num_local_heads):
+                out[0, i] = per_head_fn(i).reshape(S, D)
+            return out
+        if self._comm_stream is None:
+            self._comm_stream = torch.cuda.Stream(device=device)
+        cur = torch.cuda.current_stream(device)
+        keep = []
+        for i in range(num_local_heads):
+            o = per_head_fn(i).reshape(1, S, D)
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            keep.append(o)
+            with torch.cuda.stream(self._comm_stream):
+                self._comm_stream.wait_event(ev)
+                dist.all_gather_into_tensor(out[0, i * self.world:(i + 1) * self.world], o, group=self.group)
+        cur.wait_stream(self._comm_stream)
+        return out

@@ -32,3 +32,6 @@ cosmos_sparse_head_placement = _fwd(False)
 cosmos_hidden_states_placement = _inv(False)
 cog_sparse_head_placement = _fwd(True)
 cog_hidden_states_placement = _inv(True)
+# svg/models/cog/placement.py uses unprefixed names (cog/attention.py:12-17)
+sparse_head_placement = cog_sparse_head_placement
+hidden_states_placement = cog_hidden_states_placement
