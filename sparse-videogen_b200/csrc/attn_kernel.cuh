@@ -17,6 +17,8 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
+#include <type_traits>
+
 #include "attn_common.cuh"
 #include "ptx.cuh"
 
@@ -49,6 +51,9 @@ struct AttnBars {
 };
 
 constexpr float kRescaleTau = 8.0f;  // log2 units
+// register budget per role (launch: 384 threads x 168): warps 0-3 give registers to the 8 softmax warps
+constexpr int kRegsLight = 56;
+constexpr int kRegsSoftmax = 224;
 
 template <int D, bool BF16>
 __global__ void __launch_bounds__(384, 1)
@@ -99,6 +104,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
+    setmaxnreg_dec<kRegsLight>();
     if (lane == 0) {
       const uint32_t qbar = smem_u32(&bars->q_full);
       mbar_expect_tx(qbar, ntiles * Cfg::kTileBytes);
@@ -125,6 +131,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
+    setmaxnreg_dec<kRegsLight>();
     if (lane == 0 && nchunks > 0) {
       auto issue_qk = [&](int t, int slot, int ncols) {
         const uint32_t idesc = make_idesc(128, ncols, BF16, false, false);
@@ -207,8 +214,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
       }
       tc_commit(smem_u32(&bars->o_final));
     }
-  } else if (warp >= 4) {
+  } else if (warp < 4) {
+    setmaxnreg_dec<kRegsLight>();
+  } else {
     // ------------------------------------------------------------------ softmax / correction / epilogue
+    setmaxnreg_inc<kRegsSoftmax>();
     const int t = (warp - 4) >> 2;
     if (t < ntiles) {
       const int wq = warp & 3;
@@ -240,74 +250,101 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
         mbar_wait(sbar, j & 1, 8 + t);
         tc_fence_after();
 
-        uint32_t r[32];
-        uint32_t mbits[4];  // per 32-column group: which columns this row may attend (tail + element mask)
-        // pass 1: row max of the raw scores (the mask bits are computed here once and reused in pass 2)
-        float mx = -INFINITY;
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          if (g >= ngroups) break;
-          tmem_ld32(s_addr + g * 32, r);
-          uint32_t bits = 0xffffffffu;
-          const int left = valid - g * 32;  // columns of this group that exist
-          if (left < 32) bits = (1u << left) - 1u;
-          if (elem) bits &= mrow.bits32(kv0 + g * 32);
-          mbits[g] = bits;
+        // ---------------- single pass: the whole score row (<=128 columns) lives in registers.
+        // Compiled twice: kPlain = full unmasked 128-column chunk (the common case, no guards at all) and
+        // the general form, which first overwrites disallowed scores with -inf in place (run tails,
+        // band edges, profiling masks) -- exp2(-inf) = 0 then makes the rest identical to the plain path.
+        float rs;
+        auto chunk_body = [&](auto plain_tag) {
+          constexpr bool kPlain = decltype(plain_tag)::value;
+          uint32_t r0[32], r1[32], r2[32], r3[32];
+          tmem_ld32(s_addr, r0);
+          if (kPlain || ngroups > 1) tmem_ld32(s_addr + 32, r1);
+          if (kPlain || ngroups > 2) tmem_ld32(s_addr + 64, r2);
+          if (kPlain || ngroups > 3) tmem_ld32(s_addr + 96, r3);
           tc_wait_ld();
-          if (elem || left < 32) {  // warp-uniform
+          if constexpr (!kPlain) {
+            auto sanitize = [&](uint32_t(&rr)[32], int g) {
+              const int left = valid - g * 32;
+              if (g >= ngroups || !(elem || left < 32)) return;  // warp-uniform
+              uint32_t bits = left >= 32 ? 0xffffffffu : (1u << left) - 1u;
+              if (elem) bits &= mrow.bits32(kv0 + g * 32);
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
-              mx = fmaxf(mx, (bits >> i) & 1u ? __uint_as_float(r[i]) : -INFINITY);
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
+              for (int i = 0; i < 32; ++i) rr[i] = (bits >> i) & 1u ? rr[i] : 0xff800000u;  // -inf
+            };
+            sanitize(r0, 0);
+            sanitize(r1, 1);
+            sanitize(r2, 2);
+            sanitize(r3, 3);
           }
-        }
-        const float m_new = fmaxf(m_used, mx);
-        // lazy rescale: keep the stale reference max unless it grew by more than tau (log2 units)
-        float alpha = 1.f;
-        if ((m_new - m_used) * c > kRescaleTau) {  // false when both are -inf (NaN compare)
-          alpha = ex2_approx((m_used - m_new) * c);  // 0 when m_used == -inf
-          m_used = m_new;
-        }
-        if (j > 0 && __any_sync(0xffffffffu, alpha != 1.f)) {
-          // correction: O_row *= alpha (PV_t(j-1) is complete: the S_t(j) commit covered it)
-#pragma unroll 1
-          for (int g = 0; g < D / 32; ++g) {
-            uint32_t o[32];
-            tmem_ld32(o_addr + g * 32, o);
-            tc_wait_ld();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            tmem_st32(o_addr + g * 32, o);
-          }
-        }
-        l_run *= alpha;
-        const float mc = (m_used == -INFINITY) ? 0.f : m_used * c;
-
-        // pass 2: P = exp2(S*c - m*c) -> 16-bit, packed two per TMEM column over the S tile
-        float rs = 0.f;
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          if (g >= ngroups) break;
-          tmem_ld32(s_addr + g * 32, r);
-          tc_wait_ld();
-          const uint32_t bits = mbits[g];
-          const bool masked = elem || (valid - g * 32) < 32;  // warp-uniform
-          uint32_t pk[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            float p0 = ex2_approx(fmaf(__uint_as_float(r[2 * i]), c, -mc));
-            float p1 = ex2_approx(fmaf(__uint_as_float(r[2 * i + 1]), c, -mc));
-            if (masked) {
-              p0 = (bits >> (2 * i)) & 1u ? p0 : 0.f;
-              p1 = (bits >> (2 * i + 1)) & 1u ? p1 : 0.f;
+          auto group_max = [&](const uint32_t(&rr)[32], int g) -> float {
+            float m = -INFINITY;
+            if constexpr (!kPlain) {
+              if (g >= ngroups) return m;
             }
-            rs += p0 + p1;
-            pk[i] = pack2<BF16>(p0, p1);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) m = fmaxf(m, __uint_as_float(rr[i]));
+            return m;
+          };
+          const float mx = fmaxf(fmaxf(group_max(r0, 0), group_max(r1, 1)), fmaxf(group_max(r2, 2), group_max(r3, 3)));
+          const float m_new = fmaxf(m_used, mx);
+          // lazy rescale: keep the stale reference max unless it grew by more than tau (log2 units)
+          float alpha = 1.f;
+          if ((m_new - m_used) * c > kRescaleTau) {  // false when both are -inf (NaN compare)
+            alpha = ex2_approx((m_used - m_new) * c);  // 0 when m_used == -inf
+            m_used = m_new;
           }
-          tmem_st16(s_addr + g * 16, pk);
-        }
+          if (j > 0 && __any_sync(0xffffffffu, alpha != 1.f)) {
+            // correction: O_row *= alpha (PV_t(j-1) is complete: the S_t(j) commit covered it)
+#pragma unroll 1
+            for (int g = 0; g < D / 32; ++g) {
+              uint32_t o[32];
+              tmem_ld32(o_addr + g * 32, o);
+              tc_wait_ld();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+              tmem_st32(o_addr + g * 32, o);
+            }
+          }
+          l_run *= alpha;
+          const float mc = (m_used == -INFINITY) ? 0.f : m_used * c;
+          const uint64_t c2 = pack_f32x2(c, c), nmc2 = pack_f32x2(-mc, -mc);
+          uint64_t sum2 = pack_f32x2(0.f, 0.f);
+          // P = exp2(S*c - m*c) -> 16-bit, packed two per TMEM column over the first half of the S tile.
+          // Every 4th pair is evaluated on the FMA pipe (polynomial) to unload the MUFU.
+          auto group_p = [&](const uint32_t(&rr)[32], int g) {
+            if constexpr (!kPlain) {
+              if (g >= ngroups) return;
+            }
+            uint32_t pk[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const uint64_t x2 =
+                  ffma2(pack_f32x2(__uint_as_float(rr[2 * i]), __uint_as_float(rr[2 * i + 1])), c2, nmc2);
+              float p0, p1;
+              if ((i & 3) == 3) {
+                ex2_poly2(x2, p0, p1);
+              } else {
+                float x0, x1;
+                unpack_f32x2(x2, x0, x1);
+                p0 = ex2_approx(x0);
+                p1 = ex2_approx(x1);
+              }
+              sum2 = fadd2(sum2, pack_f32x2(p0, p1));
+              pk[i] = pack2<BF16>(p0, p1);
+            }
+            tmem_st16(s_addr + g * 16, pk);
+          };
+          group_p(r0, 0);
+          group_p(r1, 1);
+          group_p(r2, 2);
+          group_p(r3, 3);
+          float s0, s1;
+          unpack_f32x2(sum2, s0, s1);
+          rs = s0 + s1;
+        };
+        if (!elem && valid == kChunkCols) chunk_body(std::true_type{});
+        else chunk_body(std::false_type{});
         l_run += rs;
         tc_wait_st();
         tc_fence_before();

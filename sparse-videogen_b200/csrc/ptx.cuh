@@ -233,6 +233,60 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// ---- packed fp32x2 arithmetic (sm_100: one FMA-pipe instruction for two lanes)
+__device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack_f32x2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+// register re-allocation between warp roles (all warps of a warpgroup execute the same one)
+template <int N>
+__device__ __forceinline__ void setmaxnreg_inc() {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
+}
+template <int N>
+__device__ __forceinline__ void setmaxnreg_dec() {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
+}
+
+// exp2 on the FMA/ALU pipes (degree-3 minimax on [-0.5, 0.5], max rel. error 7.5e-5 -- well under
+// half an ulp of bf16/fp16 P): round x to nearest with the 1.5*2^23 trick, evaluate 2^frac, add the
+// integer part to the exponent field.  Used for a fraction of the elements to unload the MUFU.
+__device__ __forceinline__ void ex2_poly2(uint64_t x2, float& o0, float& o1) {
+  float x0, x1;
+  unpack_f32x2(x2, x0, x1);
+  x0 = fmaxf(x0, -126.f);
+  x1 = fmaxf(x1, -126.f);
+  const uint64_t xc = pack_f32x2(x0, x1);
+  const uint64_t magic = pack_f32x2(12582912.f, 12582912.f);
+  const uint64_t nmagic = pack_f32x2(-12582912.f, -12582912.f);
+  const uint64_t t = fadd2(xc, magic);            // low mantissa bits = round(x)
+  const uint64_t xr = fadd2(t, nmagic);           // round(x) as float
+  const uint64_t xf = ffma2(xr, pack_f32x2(-1.f, -1.f), xc);  // x - round(x) in [-0.5, 0.5]
+  uint64_t p = ffma2(pack_f32x2(0.055171530693769455f, 0.055171530693769455f), xf,
+                     pack_f32x2(0.2426111102104187f, 0.2426111102104187f));
+  p = ffma2(p, xf, pack_f32x2(0.6932610273361206f, 0.6932610273361206f));
+  p = ffma2(p, xf, pack_f32x2(0.9999280571937561f, 0.9999280571937561f));
+  float p0, p1, t0, t1;
+  unpack_f32x2(p, p0, p1);
+  unpack_f32x2(t, t0, t1);
+  o0 = __int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23));
+  o1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
+}
+
 // pack two fp32 -> {lo, hi} 16-bit pair (lo = first element)
 template <bool kBF16>
 __device__ __forceinline__ uint32_t pack2(float lo, float hi) {

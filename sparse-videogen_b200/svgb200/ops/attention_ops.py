@@ -3,6 +3,7 @@ text-FIRST sparse forward.  The reference runs four FlashInfer calls and merges 
 here text and video live in one variable-block map (text block x everything, video x text), one launch."""
 from __future__ import annotations
 
+import weakref
 from dataclasses import dataclass
 from typing import Optional, Tuple
 
@@ -65,9 +66,12 @@ _plan_cache: dict = {}
 
 def bsr_to_plan(indptr, indices, block_size, video_len, text_len, device) -> core.AttnPlan:
     """BSR over the video part (+ an all-to-all text prefix of `text_len`) -> one shared plan."""
-    key = (indptr.data_ptr(), indices.data_ptr(), tuple(block_size), video_len, text_len, str(device))
-    if key in _plan_cache:
-        return _plan_cache[key]
+    # cache per live BSR tensor object (a data_ptr can be recycled by the allocator: key on identity and
+    # verify through a weak reference)
+    key = (id(indptr), id(indices), tuple(block_size), video_len, text_len, str(device))
+    hit = _plan_cache.get(key)
+    if hit is not None and hit[0]() is indptr and hit[1]() is indices:
+        return hit[2]
     R, C = block_size
     MB, NB = video_len // R, video_len // C
     ip = indptr.to(device=device, dtype=torch.long)
@@ -90,7 +94,7 @@ def bsr_to_plan(indptr, indices, block_size, video_len, text_len, device) -> cor
     plan = core.plan_varblock(bm, row, col, S, ws=ws)
     plan.desc.items_stride = 0   # one map for every head: share the plan (svgb200.h, svgb_plan)
     plan.desc.counts_stride = 0
-    _plan_cache[key] = plan
+    _plan_cache[key] = (weakref.ref(indptr), weakref.ref(indices), plan)
     return plan
 
 
