@@ -134,6 +134,89 @@ class SVG1Core:
                                           self.frame_size)
         return out
 
+    def sparse_core_head_parallel(self, query, key, value, hp, sampled_rows=None, out=None, attn_events=None):
+        """Same as sparse_core on this rank's heads ([1, H_local, S, D]), with the output all-gather of every
+        head issued on a side stream as soon as that head's attention + inverse placement finished, so the
+        NVLink transfer of head i overlaps the attention of head i+1 (svgb200.parallel.HeadParallel).
+        Returns the full [1, H_local * world, S, D] output (heads interleaved: global h = i*world + rank)."""
+        cfg, Hl, S, D = query.shape
+        assert cfg == 1
+        sampled_mses = self.sample_mse(query, key, value, sampled_rows)
+        best_mask_idx = torch.argmin(sampled_mses, dim=0)
+        q_out, k_out, v_out = torch.empty_like(query), torch.empty_like(key), torch.empty_like(value)
+        self.fast_sparse_head_placement(query, key, value, q_out, k_out, v_out, best_mask_idx, self.context_length,
+                                        self.num_frame, self.frame_size)
+
+        def one_head(i):
+            if attn_events is not None:
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+            hid = self.sparse_flex_attention(q_out[:, i:i + 1], k_out[:, i:i + 1], v_out[:, i:i + 1], self.block_mask)
+            if attn_events is not None:
+                b.record()
+                attn_events.append((a, b))
+            o = torch.empty_like(hid)
+            self.fast_hidden_states_placement(hid, o, best_mask_idx[:, i:i + 1].contiguous(), self.context_length,
+                                              self.num_frame, self.frame_size)
+            return o
+
+        return hp.run_overlapped(one_head, Hl, S, D, query.dtype, query.device, out=out)
+
+    def sparse_core_from_host(self, hq, hk, hv, ho, sampled_rows=None, heads_per_stage=2):
+        """End-to-end entry for callers whose Q/K/V live in (pinned) host memory: heads are streamed through
+        a 3-stage pipeline — H2D copy of group g+1 | compute of group g | D2H copy of group g-1 — on three
+        CUDA streams, so the PCIe transfers hide behind the attention."""
+        cfg, H, S, D = hq.shape
+        assert cfg == 1
+        dev = self.block_mask.plan.ws.device
+        if not hasattr(self, "_pipe"):
+            self._pipe = {"h2d": torch.cuda.Stream(dev), "d2h": torch.cuda.Stream(dev), "bufs": {}}
+        P_ = self._pipe
+        G = heads_per_stage
+        key = (G, S, D, hq.dtype)
+        if key not in P_["bufs"]:
+            P_["bufs"][key] = [[torch.empty(1, G, S, D, dtype=hq.dtype, device=dev) for _ in range(4)] for _ in range(2)]
+        bufs = P_["bufs"][key]
+        cur = torch.cuda.current_stream(dev)
+        if sampled_rows is None:
+            sampled_rows = torch.randint(low=0, high=self.sample_mse_max_row, size=(min(self.num_sampled_rows, S),))
+        rows_dev = sampled_rows.to(dev, non_blocking=True)
+        groups = [(g0, min(H, g0 + G)) for g0 in range(0, H, G)]
+        ready, done_compute, done_d2h = {}, {}, {}
+
+        def issue_h2d(gi):
+            g0, g1 = groups[gi]
+            slot = bufs[gi & 1]
+            with torch.cuda.stream(P_["h2d"]):
+                if gi >= 2:
+                    P_["h2d"].wait_event(done_d2h[gi - 2])  # slot reuse: its output must have left first
+                for dst, src in zip(slot[:3], (hq, hk, hv)):
+                    dst[:, : g1 - g0].copy_(src[:, g0:g1], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(P_["h2d"])
+                ready[gi] = ev
+
+        issue_h2d(0)
+        for gi, (g0, g1) in enumerate(groups):
+            if gi + 1 < len(groups):
+                issue_h2d(gi + 1)
+            slot = bufs[gi & 1]
+            n = g1 - g0
+            cur.wait_event(ready[gi])
+            o = self.sparse_core(slot[0][:, :n], slot[1][:, :n], slot[2][:, :n], sampled_rows=rows_dev)
+            slot[3][:, :n].copy_(o)
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            done_compute[gi] = ev
+            with torch.cuda.stream(P_["d2h"]):
+                P_["d2h"].wait_event(ev)
+                ho[:, g0:g1].copy_(slot[3][:, :n], non_blocking=True)
+                ev2 = torch.cuda.Event()
+                ev2.record(P_["d2h"])
+                done_d2h[gi] = ev2
+        cur.wait_stream(P_["d2h"])
+        return ho
+
     def dense_core(self, query, key, value, cu_max_seqlens=None):
         seg = None
         if cu_max_seqlens is not None:

@@ -50,27 +50,41 @@ class HeadParallel:
         return out
 
     def run_overlapped(self, per_head_fn: Callable[[int], torch.Tensor], num_local_heads: int, S: int, D: int,
-                       dtype, device, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """per_head_fn(i) computes local head i ([S, D] or [1,1,S,D]) on the current stream; its all-gather
-        is issued on a side stream so it overlaps the next head's compute (CUDA / NCCL only)."""
+                       dtype, device, out: Optional[torch.Tensor] = None, compute_streams: int = 2) -> torch.Tensor:
+        """per_head_fn(i) computes local head i ([S, D] or [1,1,S,D]) on the CURRENT stream.
+
+        Heads are issued round-robin on `compute_streams` side streams, so the last partial wave of head i's
+        attention kernel is back-filled by CTAs of head i+1 (a 467-CTA launch is 3.15 waves on 148 SMs), and
+        each head's all-gather runs on a communication stream as soon as that head finished, overlapping the
+        following heads' compute (CUDA / NCCL only)."""
         H = num_local_heads * self.world
         if out is None:
             out = torch.empty(1, H, S, D, dtype=dtype, device=device)
-        if self.world == 1:
-            for i in range(num_local_heads):
-                out[0, i] = per_head_fn(i).reshape(S, D)
-            return out
+        cur = torch.cuda.current_stream(device)
         if self._comm_stream is None:
             self._comm_stream = torch.cuda.Stream(device=device)
-        cur = torch.cuda.current_stream(device)
+            self._compute_streams = [torch.cuda.Stream(device=device) for _ in range(max(1, compute_streams))]
+        start = torch.cuda.Event()
+        start.record(cur)
         keep = []
         for i in range(num_local_heads):
-            o = per_head_fn(i).reshape(1, S, D)
-            ev = torch.cuda.Event()
-            ev.record(cur)
+            cs = self._compute_streams[i % len(self._compute_streams)]
+            with torch.cuda.stream(cs):
+                cs.wait_event(start)
+                o = per_head_fn(i).reshape(1, S, D)
+                ev = torch.cuda.Event()
+                ev.record(cs)
             keep.append(o)
+            if self.world == 1:
+                with torch.cuda.stream(cs):
+                    out[0, i] = o[0]
+                continue
             with torch.cuda.stream(self._comm_stream):
                 self._comm_stream.wait_event(ev)
                 dist.all_gather_into_tensor(out[0, i * self.world:(i + 1) * self.world], o, group=self.group)
+        for cs in self._compute_streams:
+            cur.wait_stream(cs)
         cur.wait_stream(self._comm_stream)
+        for o in keep:  # tensors were produced on side streams: tell the allocator the current stream uses them
+            o.record_stream(cur)
         return out
