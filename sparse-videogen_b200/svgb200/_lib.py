@@ -8,7 +8,8 @@ import ctypes as C
 import os
 from pathlib import Path
 
-_LIB_PATH = Path(__file__).resolve().parent / "_lib" / "libsvgb200.so"
+# SVGB200_LIB lets a bring-up script A/B two builds of the same library in one process launch
+_LIB_PATH = Path(os.environ.get("SVGB200_LIB") or Path(__file__).resolve().parent / "_lib" / "libsvgb200.so")
 _lib = None
 
 

@@ -43,8 +43,13 @@ H, S, D = 24, bench.S, bench.D
 q, k, v = (torch.randn(1, H, S, D, device=dev, dtype=torch.bfloat16) for _ in range(3))
 W, _ = bench.band_width()
 plan = core.plan_band(core.MASK_HY, bench.F * bench.P, bench.F * bench.P + bench.PROMPT_LEN, W, H, S, dev)
-ms = t(lambda: core.attn_fwd(q, k, v, plan))
-emit(case="band_hy_rho0.30", ms=ms, tflops=4.0 * D * bench.band_pairs(W) * H / ms / 1e9)
+for tune in os.environ.get("PERF_TUNES", "").split(","):
+    if tune:
+        os.environ["SVGB_ATTN_TUNE"] = tune
+    ms = t(lambda: core.attn_fwd(q, k, v, plan))
+    emit(case="band_hy_rho0.30", tune=tune, ms=ms, tflops=4.0 * D * bench.band_pairs(W) * H / ms / 1e9)
+if os.environ.get("PERF_BAND_ONLY"):
+    sys.exit(0)
 
 g = torch.Generator().manual_seed(0)
 

@@ -20,7 +20,7 @@ if os.environ.get("PROFILE_MODE", "band") == "band":
     W, _ = bench.band_width()
     plan = core.plan_band(core.MASK_HY, bench.F * bench.P, bench.F * bench.P + bench.PROMPT_LEN, W, H, S, dev)
 else:
-    QC, KC = 465, 931
+    QC, KC = (int(x) for x in os.environ.get("PROFILE_QCKC", "465,931").split(","))
     g = torch.Generator().manual_seed(0)
 
     def sizes(n):
