@@ -56,19 +56,27 @@ dynmap_kernel(const uint16_t* __restrict__ qc, const uint16_t* __restrict__ kc, 
   __syncthreads();
   const float sqrt_d = static_cast<float>(sqrt(static_cast<double>(D)));
   float mx = -INFINITY;
-  for (int j = threadIdx.x; j < KC; j += blockDim.x) {
-    const uint32_t* kr = reinterpret_cast<const uint32_t*>(kc + (static_cast<size_t>(bh) * KC + j) * D);
-    float acc = 0.f;
-    for (int d2 = 0; d2 < D / 2; ++d2) {
-      const uint32_t w = __ldg(kr + d2);
-      acc = fmaf(qrow[2 * d2], h2f<BF16>(static_cast<uint16_t>(w & 0xffff)), acc);
-      acc = fmaf(qrow[2 * d2 + 1], h2f<BF16>(static_cast<uint16_t>(w >> 16)), acc);
+  // one warp per key centroid: a coalesced 2*D-byte row read, lanes stride the row in 32-bit pairs,
+  // fixed-order butterfly reduction (deterministic).  All QC rows of a head re-read kc from L2.
+  {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    for (int j = warp; j < KC; j += nwarps) {
+      const uint32_t* kr = reinterpret_cast<const uint32_t*>(kc + (static_cast<size_t>(bh) * KC + j) * D);
+      float acc = 0.f;
+      for (int d2 = lane; d2 < D / 2; d2 += 32) {
+        const uint32_t w = __ldg(kr + d2);
+        acc = fmaf(qrow[2 * d2], h2f<BF16>(static_cast<uint16_t>(w & 0xffff)), acc);
+        acc = fmaf(qrow[2 * d2 + 1], h2f<BF16>(static_cast<uint16_t>(w >> 16)), acc);
+      }
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (lane == 0) {
+        const float m = h2f<BF16>(f2h<BF16>(acc));
+        sc[j] = h2f<BF16>(f2h<BF16>(m / sqrt_d));
+      }
     }
-    const float m = h2f<BF16>(f2h<BF16>(acc));
-    const float s = h2f<BF16>(f2h<BF16>(m / sqrt_d));
-    sc[j] = s;
-    mx = fmaxf(mx, s);
   }
+  __syncthreads();
+  for (int j = threadIdx.x; j < KC; j += blockDim.x) mx = fmaxf(mx, sc[j]);
   mx = block_reduce(mx, red, true);
   float part = 0.f;
   for (int j = threadIdx.x; j < KC; j += blockDim.x) {

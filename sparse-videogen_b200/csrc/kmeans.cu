@@ -190,21 +190,33 @@ kmeans_assign_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_cons
         tc_fence_after();
         const float* cs = csq + j * 128;
         const int kbase = j * 128;
+        const bool tail = kbase + 128 > K;  // only the last chunk has centroid columns past K
 #pragma unroll 1
         for (int g = 0; g < 4; ++g) {
           uint32_t r[32];
           tmem_ld32(lane_addr + buf * 128 + g * 32, r);
           tc_wait_ld();
+          // d = (|x|^2 + |c|^2) - 2 x.c  (one rounding for the sum, one for the fma, as the reference);
+          // min_k max(d_k, 0) == max(min_k d_k, 0), so the clamp is applied once to the group minimum and
+          // the running (best, argbest) is only touched when the group improves it -- O(log K) times per
+          // point -- which takes the compare/select pair out of the per-element work.
+          float dv[32];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const int kidx = kbase + g * 32 + i;
-            float d = fmaf(-2.f, __uint_as_float(r[i]), xs + cs[g * 32 + i]);
-            d = fmaxf(d, 0.f);
-            if (kidx >= K) d = 3.4e38f;
-            if (d < best) {
-              best = d;
-              best_k = kidx;
-            }
+          for (int i = 0; i < 32; ++i) dv[i] = fmaf(-2.f, __uint_as_float(r[i]), xs + cs[g * 32 + i]);
+          if (tail) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (kbase + g * 32 + i >= K) dv[i] = 3.4e38f;
+          }
+          float gmin = dv[0];
+#pragma unroll
+          for (int i = 1; i < 32; ++i) gmin = fminf(gmin, dv[i]);
+          gmin = fmaxf(gmin, 0.f);
+          if (gmin < best) {  // strict: an earlier group keeps ties; inside the group the lowest index wins
+            best = gmin;
+#pragma unroll
+            for (int i = 31; i >= 0; --i)
+              if (fmaxf(dv[i], 0.f) == gmin) best_k = kbase + g * 32 + i;
           }
         }
         tc_fence_before();
@@ -222,8 +234,10 @@ kmeans_assign_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_cons
 }
 
 // ---------------------------------------------------------------------------------------------
-// update: one CTA per (head, cluster); members = perm[off .. off+cnt) (ascending token index)
-// 256 threads = 4 row-groups x 64 threads (2 dims each, D=128) ; fixed-order combine
+// update: one CTA per (head, cluster); members = perm[off .. off+cnt) (ascending token index).
+// 256 threads = 16 row-groups x (D/8) lanes, each lane owns 8 consecutive dims (one 16-byte load per
+// member row); group g sums members g, g+16, ... in order, then the 16 partials are combined in a fixed
+// order -> run-to-run deterministic (the reference's fp32 atomics are not).
 // ---------------------------------------------------------------------------------------------
 template <bool BF16>
 __global__ void __launch_bounds__(256)
@@ -242,68 +256,54 @@ kmeans_update_kernel(const uint16_t* __restrict__ x, const int* __restrict__ per
   const int k = blockIdx.x, bh = blockIdx.y;
   const int cnt = counts[static_cast<size_t>(bh) * K + k];
   const int off = chunk0_base[static_cast<size_t>(bh) * K + k];  // exclusive prefix of counts
-  const int dpairs = D / 2;                                       // 32-bit words per row
-  const int groups = blockDim.x / dpairs;
-  const int grp = threadIdx.x / dpairs, w = threadIdx.x % dpairs;
-  __shared__ float2 part[8][64];
-  __shared__ float s_norm[64];
-  float2 acc = make_float2(0.f, 0.f);
+  const int lanes = D / 8;                                        // 16-byte vectors per row
+  const int groups = blockDim.x / lanes;
+  const int grp = threadIdx.x / lanes, w = threadIdx.x % lanes;
+  __shared__ float part[32][129];
+  __shared__ float s_norm[128];
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  auto add_row = [&](const uint4& v) {
+    const uint32_t ws[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      acc[2 * i] += to_f32<BF16>(static_cast<uint16_t>(ws[i] & 0xffff));
+      acc[2 * i + 1] += to_f32<BF16>(static_cast<uint16_t>(ws[i] >> 16));
+    }
+  };
   if (grp < groups) {
     const int* pp = perm + static_cast<size_t>(bh) * N + off;
-    const uint32_t* xb = reinterpret_cast<const uint32_t*>(x) + static_cast<size_t>(bh) * N * dpairs;
+    const uint4* xb = reinterpret_cast<const uint4*>(x) + static_cast<size_t>(bh) * N * lanes;
     int i = grp;
     for (; i + 3 * groups < cnt; i += 4 * groups) {
-      uint32_t v[4];
+      uint4 v[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) v[u] = __ldg(xb + static_cast<size_t>(__ldg(pp + i + u * groups)) * dpairs + w);
+      for (int u = 0; u < 4; ++u) v[u] = __ldg(xb + static_cast<size_t>(__ldg(pp + i + u * groups)) * lanes + w);
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        acc.x += to_f32<BF16>(static_cast<uint16_t>(v[u] & 0xffff));
-        acc.y += to_f32<BF16>(static_cast<uint16_t>(v[u] >> 16));
-      }
+      for (int u = 0; u < 4; ++u) add_row(v[u]);
     }
-    for (; i < cnt; i += groups) {
-      const uint32_t v = __ldg(xb + static_cast<size_t>(__ldg(pp + i)) * dpairs + w);
-      acc.x += to_f32<BF16>(static_cast<uint16_t>(v & 0xffff));
-      acc.y += to_f32<BF16>(static_cast<uint16_t>(v >> 16));
-    }
-    part[grp][w] = acc;
+    for (; i < cnt; i += groups) add_row(__ldg(xb + static_cast<size_t>(__ldg(pp + i)) * lanes + w));
+#pragma unroll
+    for (int e = 0; e < 8; ++e) part[grp][w * 8 + e] = acc[e];
   }
   __syncthreads();
-  if (threadIdx.x < dpairs) {
-    float2 s = make_float2(0.f, 0.f);
-    for (int gI = 0; gI < groups; ++gI) {
-      s.x += part[gI][w].x;
-      s.y += part[gI][w].y;
-    }
-    const uint32_t oldw = reinterpret_cast<const uint32_t*>(c_old)[(static_cast<size_t>(bh) * K + k) * dpairs + w];
-    const float o0 = to_f32<BF16>(static_cast<uint16_t>(oldw & 0xffff));
-    const float o1 = to_f32<BF16>(static_cast<uint16_t>(oldw >> 16));
-    float n0, n1;
-    if (cnt > 0) {
-      const float denom = static_cast<float>(cnt);
-      n0 = round16<BF16>(s.x / denom);
-      n1 = round16<BF16>(s.y / denom);
-    } else {
-      n0 = o0;
-      n1 = o1;
-    }
-    uint32_t packed;
-    if constexpr (BF16) {
-      packed = (__float_as_uint(n0) >> 16) | (__float_as_uint(n1) & 0xffff0000u);
-    } else {
-      packed = static_cast<uint32_t>(__half_as_ushort(__float2half_rn(n0))) |
-               (static_cast<uint32_t>(__half_as_ushort(__float2half_rn(n1))) << 16);
-    }
-    reinterpret_cast<uint32_t*>(c_new)[(static_cast<size_t>(bh) * K + k) * dpairs + w] = packed;
+  if (static_cast<int>(threadIdx.x) < D) {
+    const int d = threadIdx.x;
+    float s = 0.f;
+    for (int gI = 0; gI < groups; ++gI) s += part[gI][d];
+    const float o = to_f32<BF16>(c_old[(static_cast<size_t>(bh) * K + k) * D + d]);
+    const float n = cnt > 0 ? round16<BF16>(s / static_cast<float>(cnt)) : o;
+    uint16_t bits;
+    if constexpr (BF16) bits = static_cast<uint16_t>(__float_as_uint(n) >> 16);
+    else bits = __half_as_ushort(__float2half_rn(n));
+    c_new[(static_cast<size_t>(bh) * K + k) * D + d] = bits;
     // shift = |round16(new - old)|_2, then rounded to 16 bit like the reference's bf16 tensor ops
-    const float d0 = round16<BF16>(n0 - o0), d1 = round16<BF16>(n1 - o1);
-    s_norm[w] = d0 * d0 + d1 * d1;
+    const float dd = round16<BF16>(n - o);
+    s_norm[d] = dd * dd;
   }
   __syncthreads();
   if (threadIdx.x == 0 && shift_max) {
     float t = 0.f;
-    for (int i = 0; i < dpairs; ++i) t += s_norm[i];
+    for (int i = 0; i < D; ++i) t += s_norm[i];
     const float nrm = round16<BF16>(sqrtf(t));
     atomicMax(reinterpret_cast<int*>(shift_max), __float_as_int(nrm));  // non-negative floats order as ints
   }
@@ -423,7 +423,7 @@ static int launch_update(const void* x, const int* perm, const int* counts, cons
                          const void* c_old1, void* c_new0, void* c_new1, float* shift_max, int BH, int N, int K,
                          int D, int dtype, const KmState* st, cudaStream_t stream) {
   dim3 grid(K, BH);
-  const int threads = 2 * D;  // 4 row-groups of D/2 threads
+  const int threads = 256;  // 16 (D=128) or 32 (D=64) row-groups of D/8 lanes
   auto X = static_cast<const uint16_t*>(x);
   auto O0 = static_cast<const uint16_t*>(c_old0);
   auto O1 = static_cast<const uint16_t*>(c_old1);
