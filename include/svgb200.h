@@ -44,7 +44,7 @@ int svgb_device_check(int* sm_major, int* sm_minor, int* num_sms);
 /* Host-side descriptor of a device-resident plan (filled by the plan functions, read by
  * svgb_attn_fwd).  Plain data; copyable. */
 typedef struct svgb_plan {
-  int32_t kind;          /* 1 = variable-block, 2 = band */
+  int32_t kind;          /* 1 = variable-block (TMA chunks), 2 = band, 3 = variable-block (row gather) */
   int32_t BH, S;
   int32_t max_items;     /* grid.x of the attention launch */
   int32_t items_stride;  /* 0 when one plan serves every head */
@@ -52,7 +52,10 @@ typedef struct svgb_plan {
   int32_t mask_mode, m0, m1, m2;
   int64_t counts_off, items_off, chunks_off; /* byte offsets inside the plan workspace */
   int64_t bytes;
+  int64_t aux_off;       /* kind 3: per-item selected-key totals */
 } svgb_plan;
+/* A plan built with BH == 1 may serve every head of a launch (one map for all heads, e.g. BSR masks):
+ * set items_stride = counts_stride = 0 in the host struct. */
 
 /* SVG2 / BSR / dense: q-block i of head h attends k-block j iff map[h,i,j] != 0.
  * Stands behind dynamic_block_sparse_fwd_flashinfer's wrapper.plan (svg/kmeans_utils.py:1355-1385).
@@ -62,6 +65,14 @@ int svgb_attn_plan_varblock_bytes(int BH, int S, int QC, int KC, size_t* bytes);
 int svgb_attn_plan_varblock(const uint8_t* map, const int32_t* row_sz, const int32_t* col_sz, int BH,
                             int S, int QC, int KC, void* plan_ws, size_t ws_bytes, svgb_plan* plan,
                             void* stream);
+
+/* Same map, lowered for the row-gather kernel path: the selected key ranges are kept as runs and the
+ * kernel gathers exactly-full 128-key chunks across run boundaries with cp.async (no padded tail chunk per
+ * run), optionally through row-index vectors (svgb_attn_fwd_gather) so the cluster permutation of Q, K, V
+ * (permute_tensor_by_labels_triton x3, svg/models/hyvideo/attention.py:651-653) never materialises. */
+int svgb_attn_plan_varblock_gather(const uint8_t* map, const int32_t* row_sz, const int32_t* col_sz, int BH,
+                                   int S, int QC, int KC, void* plan_ws, size_t ws_bytes, svgb_plan* plan,
+                                   void* stream);
 
 /* SVG1: one element-exact band mask shared by every head.  Stands behind prepare_flexattention /
  * create_block_mask (svg/models/hyvideo/attention.py:527-551). */
@@ -87,6 +98,16 @@ int svgb_attn_fwd(const void* q, const void* k, const void* v, void* o, float* l
                   const int32_t* o_rows, int dtype, int BH, int S, int D, long long row_stride,
                   long long head_stride, long long o_row_stride, long long o_head_stride,
                   float sm_scale, const svgb_plan* plan, const void* plan_ws, void* stream);
+
+/* Gather form (plan from svgb_attn_plan_varblock_gather).  Row r of the plan's (cluster-sorted) query order
+ * is read from q[h, q_rows[h,r]] (q_rows NULL: identity), key/value row r from k/v[h, kv_rows[h,r]], and the
+ * output row is written to o[h, o_rows[h,r]] — pass the argsort of the q-labels as q_rows AND o_rows and the
+ * argsort of the k-labels as kv_rows to run SVG2 attention directly on the un-permuted tensors. */
+int svgb_attn_fwd_gather(const void* q, const void* k, const void* v, void* o, float* lse,
+                         const int32_t* q_rows, const int32_t* kv_rows, const int32_t* o_rows, int dtype,
+                         int BH, int S, int D, long long row_stride, long long head_stride,
+                         long long o_row_stride, long long o_head_stride, float sm_scale,
+                         const svgb_plan* plan, const void* plan_ws, void* stream);
 
 /* density of a variable-block map (density_calculation, svg/kmeans_utils.py:13-31) -> float [BH] */
 int svgb_density(const uint8_t* map, const int32_t* row_sz, const int32_t* col_sz, int BH, int QC,

@@ -143,6 +143,17 @@ struct AttnArgs {
   int mask_mode, m0, m1, m2;
   const int* q_index;       // optional [S]: query position used by the element mask (sampled rows)
   int out_f32;              // 1: o is fp32 (used for split-KV partials)
+  // ---- gather mode (SVG2): `chunks` holds RUNS {src_start, cum_before} (+ a sentinel {0, total}) of the
+  // selected key ranges; K/V rows are gathered with cp.async into exactly-full 128-token chunks, optionally
+  // through row-index vectors so the cluster permutation of Q, K, V never materialises in HBM.
+  int gather;
+  const int* item_total;    // [BH * items_stride | items]: selected keys per item
+  const int* q_rows;        // optional [BH, S]: source row of (permuted) query row
+  const int* kv_rows;       // optional [BH, S]: source row of (permuted) key/value row
+  const void* q_ptr;        // raw tensors for the gather path ([BH,S,D] with the strides below)
+  const void* k_ptr;
+  const void* v_ptr;
+  long long in_row_stride, in_head_stride;  // elements
 };
 
 }  // namespace svgb

@@ -14,7 +14,10 @@ namespace svgb {
 __global__ void plan_varblock_kernel(const uint8_t* __restrict__ map, const int* __restrict__ row_sz,
                                      const int* __restrict__ col_sz, int QC, int KC, int max_items,
                                      int chunk_cap, int* __restrict__ counts, int4* __restrict__ items,
-                                     int2* __restrict__ chunks) {
+                                     int2* __restrict__ chunks, int* __restrict__ item_total) {
+  // item_total != nullptr selects the gather form: the list holds RUNS {start, keys before this run} plus a
+  // sentinel {0, total}; the kernel then gathers exactly-full 128-key chunks across run boundaries.
+  const bool gather = item_total != nullptr;
   extern __shared__ int sm[];
   int* coloff = sm;                 // KC + 1
   int* rowoff = coloff + KC + 1;    // QC + 1
@@ -50,7 +53,7 @@ __global__ void plan_varblock_kernel(const uint8_t* __restrict__ map, const int*
     const size_t list = (static_cast<size_t>(bh) * QC + qb) * chunk_cap;
     int2* out = chunks + list;
     const uint8_t* mrow = map + (static_cast<size_t>(bh) * QC + qb) * KC;
-    int n = 0;
+    int n = 0, total = 0;
     int run_s = -1, run_e = -1;
     for (int j = 0; j <= KC; ++j) {
       bool sel = false;
@@ -65,9 +68,14 @@ __global__ void plan_varblock_kernel(const uint8_t* __restrict__ map, const int*
         continue;
       }
       if (run_s >= 0 && (sel || j == KC)) {
-        for (int p = run_s; p < run_e && n < chunk_cap; p += kChunkCols) {
-          const int valid = min(kChunkCols, run_e - p);
-          out[n++] = make_int2(p, chunk_meta(valid, false));
+        if (gather) {
+          if (n < chunk_cap - 1) out[n++] = make_int2(run_s, total);
+          total += run_e - run_s;
+        } else {
+          for (int p = run_s; p < run_e && n < chunk_cap; p += kChunkCols) {
+            const int valid = min(kChunkCols, run_e - p);
+            out[n++] = make_int2(p, chunk_meta(valid, false));
+          }
         }
         run_s = -1;
       }
@@ -76,13 +84,16 @@ __global__ void plan_varblock_kernel(const uint8_t* __restrict__ map, const int*
         run_e = e;
       }
     }
+    if (gather) out[n] = make_int2(0, total);  // sentinel: ends the last run
     const int nit = (r + kItemRows - 1) / kItemRows;
     for (int t = 0; t < nit; ++t) {
       const int idx = itembase[qb] + t;
-      if (idx < max_items)
+      if (idx < max_items) {
         items[static_cast<size_t>(bh) * max_items + idx] =
             make_int4(rowoff[qb] + t * kItemRows, min(kItemRows, r - t * kItemRows),
                       static_cast<int>(list), n);
+        if (gather) item_total[static_cast<size_t>(bh) * max_items + idx] = total;
+      }
     }
   }
 }
@@ -305,9 +316,15 @@ template <int D, bool BF16>
 static int launch_attn(const CUtensorMap& qm, const CUtensorMap& km, const CUtensorMap& vm,
                        const AttnArgs& args, dim3 grid, cudaStream_t stream) {
   using Cfg = AttnCfg<D>;
-  auto kern = attn_fwd_kernel<D, BF16>;
-  SVGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-  kern<<<grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(qm, km, vm, args);
+  if (args.gather) {
+    auto kern = attn_fwd_kernel<D, BF16, true>;
+    SVGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    kern<<<grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(qm, km, vm, args);
+  } else {
+    auto kern = attn_fwd_kernel<D, BF16, false>;
+    SVGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    kern<<<grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(qm, km, vm, args);
+  }
   SVGB_LAUNCH_OK();
   return 0;
 }
@@ -356,13 +373,14 @@ int svgb_attn_plan_varblock_bytes(int BH, int S, int QC, int KC, size_t* bytes) 
   const size_t counts = align_up(sizeof(int) * BH, 256);
   const size_t items = align_up(sizeof(int4) * BH * varblock_max_items(S, QC), 256);
   const size_t chunks = align_up(sizeof(int2) * static_cast<size_t>(BH) * QC * varblock_chunk_cap(S, KC), 256);
-  *bytes = counts + items + chunks;
+  const size_t aux = align_up(sizeof(int) * BH * varblock_max_items(S, QC), 256);  // gather plans: keys per item
+  *bytes = counts + items + chunks + aux;
   return 0;
 }
 
-int svgb_attn_plan_varblock(const uint8_t* map, const int32_t* row_sz, const int32_t* col_sz, int BH,
-                            int S, int QC, int KC, void* plan_ws, size_t ws_bytes, svgb_plan* plan,
-                            void* stream) {
+static int plan_varblock_impl(const uint8_t* map, const int32_t* row_sz, const int32_t* col_sz, int BH,
+                              int S, int QC, int KC, void* plan_ws, size_t ws_bytes, svgb_plan* plan,
+                              void* stream, bool gather) {
   size_t need = 0;
   if (svgb_attn_plan_varblock_bytes(BH, S, QC, KC, &need)) return -1;
   SVGB_REQUIRE(map && row_sz && col_sz && plan_ws && plan, "null pointer");
@@ -371,26 +389,41 @@ int svgb_attn_plan_varblock(const uint8_t* map, const int32_t* row_sz, const int
                "plan too large for 32-bit chunk offsets");
   const int max_items = varblock_max_items(S, QC);
   const int cap = varblock_chunk_cap(S, KC);
-  plan->kind = 1;
+  plan->kind = gather ? 3 : 1;
   plan->BH = BH;
   plan->S = S;
   plan->max_items = max_items;
   plan->items_stride = max_items;
   plan->counts_stride = 1;
   plan->mask_mode = MASK_NONE;
-  plan->m0 = plan->m1 = plan->m2 = 0;
+  plan->m0 = gather ? (KC + 1) / 2 + 1 : 0;  // gather: upper bound of runs per q-block (kernel smem table)
+  plan->m1 = plan->m2 = 0;
   plan->counts_off = 0;
   plan->items_off = align_up(sizeof(int) * BH, 256);
   plan->chunks_off = plan->items_off + align_up(sizeof(int4) * BH * max_items, 256);
+  plan->aux_off = plan->chunks_off + align_up(sizeof(int2) * static_cast<size_t>(BH) * QC * cap, 256);
   plan->bytes = need;
   char* ws = static_cast<char*>(plan_ws);
   const size_t smem = sizeof(int) * (KC + 1 + 2 * (QC + 1));
   SVGB_REQUIRE(smem <= 48 * 1024, "QC/KC too large for the plan kernel (%zu B smem)", smem);
   plan_varblock_kernel<<<BH, 256, smem, static_cast<cudaStream_t>(stream)>>>(
       map, row_sz, col_sz, QC, KC, max_items, cap, reinterpret_cast<int*>(ws + plan->counts_off),
-      reinterpret_cast<int4*>(ws + plan->items_off), reinterpret_cast<int2*>(ws + plan->chunks_off));
+      reinterpret_cast<int4*>(ws + plan->items_off), reinterpret_cast<int2*>(ws + plan->chunks_off),
+      gather ? reinterpret_cast<int*>(ws + plan->aux_off) : nullptr);
   SVGB_LAUNCH_OK();
   return 0;
+}
+
+int svgb_attn_plan_varblock(const uint8_t* map, const int32_t* row_sz, const int32_t* col_sz, int BH,
+                            int S, int QC, int KC, void* plan_ws, size_t ws_bytes, svgb_plan* plan,
+                            void* stream) {
+  return plan_varblock_impl(map, row_sz, col_sz, BH, S, QC, KC, plan_ws, ws_bytes, plan, stream, false);
+}
+
+int svgb_attn_plan_varblock_gather(const uint8_t* map, const int32_t* row_sz, const int32_t* col_sz, int BH,
+                                   int S, int QC, int KC, void* plan_ws, size_t ws_bytes, svgb_plan* plan,
+                                   void* stream) {
+  return plan_varblock_impl(map, row_sz, col_sz, BH, S, QC, KC, plan_ws, ws_bytes, plan, stream, true);
 }
 
 int svgb_attn_plan_band_bytes(int S, size_t* bytes) {
@@ -427,6 +460,7 @@ int svgb_attn_plan_band(int mask_mode, int m0, int m1, int m2, int BH, int S, vo
   plan->counts_off = 0;
   plan->items_off = 256;
   plan->chunks_off = 256 + align_up(sizeof(int4) * n_items_cap, 256);
+  plan->aux_off = 0;
   plan->bytes = need;
   char* ws = static_cast<char*>(plan_ws);
   plan_band_kernel<<<n_items, kItemRows, 0, static_cast<cudaStream_t>(stream)>>>(
@@ -436,10 +470,11 @@ int svgb_attn_plan_band(int mask_mode, int m0, int m1, int m2, int BH, int S, vo
   return 0;
 }
 
-int svgb_attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse,
-                  const int32_t* o_rows, int dtype, int BH, int S, int D, long long row_stride,
-                  long long head_stride, long long o_row_stride, long long o_head_stride,
-                  float sm_scale, const svgb_plan* plan, const void* plan_ws, void* stream) {
+static int attn_fwd_entry(const void* q, const void* k, const void* v, void* o, float* lse,
+                          const int32_t* q_rows, const int32_t* kv_rows, const int32_t* o_rows, int dtype, int BH,
+                          int S, int D, long long row_stride, long long head_stride, long long o_row_stride,
+                          long long o_head_stride, float sm_scale, const svgb_plan* plan, const void* plan_ws,
+                          void* stream) {
   SVGB_REQUIRE(q && k && v && o && plan && plan_ws, "null pointer");
   SVGB_REQUIRE(D == 64 || D == 128, "head_dim %d unsupported (64 or 128)", D);
   SVGB_REQUIRE(dtype == SVGB_BF16 || dtype == SVGB_F16, "dtype %d unsupported", dtype);
@@ -447,6 +482,8 @@ int svgb_attn_fwd(const void* q, const void* k, const void* v, void* o, float* l
                "plan was built for BH=%d S=%d, called with BH=%d S=%d", plan->BH, plan->S, BH, S);
   SVGB_REQUIRE((reinterpret_cast<uintptr_t>(o) & 15) == 0 && o_row_stride % 8 == 0 && o_head_stride % 8 == 0,
                "output must be 16-byte aligned with strides multiple of 8 elements");
+  SVGB_REQUIRE(plan->kind == 3 || (!q_rows && !kv_rows), "row gathers need a plan from svgb_attn_plan_varblock_gather");
+  SVGB_REQUIRE(plan->kind != 3 || plan->m0 <= AttnCfg<64>::kMaxRunsSmem, "gather plan has too many runs per q-block (%d)", plan->m0);
   const char* ws = static_cast<const char*>(plan_ws);
   AttnArgs a;
   a.items = reinterpret_cast<const int4*>(ws + plan->items_off);
@@ -467,8 +504,34 @@ int svgb_attn_fwd(const void* q, const void* k, const void* v, void* o, float* l
   a.m2 = plan->m2;
   a.q_index = nullptr;
   a.out_f32 = 0;
+  a.gather = plan->kind == 3 ? 1 : 0;
+  a.item_total = plan->kind == 3 ? reinterpret_cast<const int*>(ws + plan->aux_off) : nullptr;
+  a.q_rows = q_rows;
+  a.kv_rows = kv_rows;
+  a.q_ptr = q;
+  a.k_ptr = k;
+  a.v_ptr = v;
+  a.in_row_stride = row_stride;
+  a.in_head_stride = head_stride;
   return attn_fwd_impl(q, S, row_stride, head_stride, k, v, S, row_stride, head_stride, dtype, BH, D, a,
                        plan->max_items, static_cast<cudaStream_t>(stream));
+}
+
+int svgb_attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse,
+                  const int32_t* o_rows, int dtype, int BH, int S, int D, long long row_stride,
+                  long long head_stride, long long o_row_stride, long long o_head_stride,
+                  float sm_scale, const svgb_plan* plan, const void* plan_ws, void* stream) {
+  return attn_fwd_entry(q, k, v, o, lse, nullptr, nullptr, o_rows, dtype, BH, S, D, row_stride, head_stride,
+                        o_row_stride, o_head_stride, sm_scale, plan, plan_ws, stream);
+}
+
+int svgb_attn_fwd_gather(const void* q, const void* k, const void* v, void* o, float* lse, const int32_t* q_rows,
+                         const int32_t* kv_rows, const int32_t* o_rows, int dtype, int BH, int S, int D,
+                         long long row_stride, long long head_stride, long long o_row_stride,
+                         long long o_head_stride, float sm_scale, const svgb_plan* plan, const void* plan_ws,
+                         void* stream) {
+  return attn_fwd_entry(q, k, v, o, lse, q_rows, kv_rows, o_rows, dtype, BH, S, D, row_stride, head_stride,
+                        o_row_stride, o_head_stride, sm_scale, plan, plan_ws, stream);
 }
 
 int svgb_density(const uint8_t* map, const int32_t* row_sz, const int32_t* col_sz, int BH, int QC,

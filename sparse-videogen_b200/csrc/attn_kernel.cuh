@@ -31,6 +31,9 @@ struct AttnCfg {
   static constexpr int kPanelBytes = 128 * 128;          // 128 rows x 128 B
   static constexpr int kTileBytes = kPanelBytes * kHalves;
   static constexpr int kStages = (D == 128) ? 5 : 8;
+  // gather instantiation: one stage less; the freed tile holds the item's run table in shared memory
+  static constexpr int kStagesGather = kStages;
+  static constexpr int kMaxRunsSmem = kTileBytes / 8 - 1;
   static constexpr int kQBytes = 2 * kTileBytes;
   static constexpr int kRingBytes = kStages * kTileBytes;
   static constexpr int kBarBytes = 1024;
@@ -52,10 +55,12 @@ struct AttnBars {
 
 constexpr float kRescaleTau = 8.0f;  // log2 units
 // register budget per role (launch: 384 threads x 168): warps 0-3 give registers to the 8 softmax warps
-constexpr int kRegsLight = 56;
+constexpr int kRegsLight = 56;   // 128 x 56 + 256 x 224 = 64512 = the launch allocation (384 x 168)
 constexpr int kRegsSoftmax = 224;
 
-template <int D, bool BF16>
+// kGather selects the producer: false = TMA boxes over contiguous key ranges (chunk list), true = cp.async
+// row gathers over a run list (separate instantiations keep each one's register footprint small).
+template <int D, bool BF16, bool kGather>
 __global__ void __launch_bounds__(384, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant__ CUtensorMap kmap,
                 const __grid_constant__ CUtensorMap vmap, const AttnArgs args) {
@@ -64,9 +69,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
   const int n_items = args.item_count[bh * args.counts_stride];
   if (static_cast<int>(blockIdx.x) >= n_items) return;
   const int4 item = args.items[static_cast<size_t>(bh) * args.items_stride + blockIdx.x];
-  const int q_row0 = item.x, nrows = item.y, chunk0 = item.z, nchunks = item.w;
+  const int q_row0 = item.x, nrows = item.y, chunk0 = item.z;
   const int ntiles = nrows > kTileRows ? 2 : 1;
   const int2* __restrict__ chunks = args.chunks + chunk0;
+  constexpr bool gather = kGather;
+  // gather mode: item.w = number of runs, chunks are implicit (128 selected keys each, last one partial)
+  const int nruns = gather ? item.w : 0;
+  const int total_kv = gather ? args.item_total[static_cast<size_t>(bh) * args.items_stride + blockIdx.x] : 0;
+  const int nchunks = gather ? (total_kv + kChunkCols - 1) / kChunkCols : item.w;
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -74,6 +84,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
   const uint32_t sQ = smem_base;
   const uint32_t sRing = smem_base + Cfg::kQBytes;
   AttnBars* bars = reinterpret_cast<AttnBars*>(smem_al + Cfg::kQBytes + Cfg::kRingBytes);
+  constexpr int kStages = kGather ? Cfg::kStagesGather : Cfg::kStages;
+  // gather: the run table {src_start, keys_before} (+ sentinel) stays in global memory; it is a few KB per
+  // item, re-read by every producer lane, and therefore L1-resident after the first chunk
+  const int2* __restrict__ s_runs = chunks;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -84,14 +98,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
     tma_prefetch_desc(&vmap);
   }
   if (warp == 1 && lane == 0) {
-    mbar_init(smem_u32(&bars->q_full), 1);
+    const uint32_t n_prod = gather ? 3u : 1u;  // gather: one arrival per producer warp (0, 2, 3)
+    mbar_init(smem_u32(&bars->q_full), n_prod);
     mbar_init(smem_u32(&bars->o_final), 1);
     for (int t = 0; t < 2; ++t) {
       mbar_init(smem_u32(&bars->s_full[t]), 1);
       mbar_init(smem_u32(&bars->p_full[t]), 128);
     }
-    for (int s = 0; s < Cfg::kStages; ++s) {
-      mbar_init(smem_u32(&bars->kv_full[s]), 1);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(smem_u32(&bars->kv_full[s]), n_prod);
       mbar_init(smem_u32(&bars->kv_empty[s]), 1);
     }
     mbar_fence_init();
@@ -102,7 +117,119 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem = bars->tmem_base;
 
-  if (warp == 0) {
+  if (gather && (warp == 0 || warp == 2 || warp == 3)) {
+    // ------------------------------------------------------------------ cp.async gather producers
+    // 3 warps = 6 half-warps; a half-warp moves one 2*D-byte row per step (16 lanes x 16 B, coalesced),
+    // writing the 128-byte-swizzled K-major / MN-major image the UMMA descriptors expect:
+    //   piece p (16 B) of row r  ->  panel p/8, byte r*128 + ((p%8) ^ (r%8))*16.
+    setmaxnreg_dec<kRegsLight>();
+    const int pw = warp == 0 ? 0 : warp - 1;
+    const int hw = pw * 2 + (lane >> 4);   // half-warp id 0..5
+    const int pl = lane & 15;              // 16-byte piece within the row
+    constexpr int kPieces = D / 8;         // pieces per row (8 or 16)
+    const bool lane_live = pl < kPieces;
+    const uint16_t* qp = static_cast<const uint16_t*>(args.q_ptr) + bh * args.in_head_stride;
+    const uint16_t* kp = static_cast<const uint16_t*>(args.k_ptr) + bh * args.in_head_stride;
+    const uint16_t* vp = static_cast<const uint16_t*>(args.v_ptr) + bh * args.in_head_stride;
+    const int* q_rows = args.q_rows ? args.q_rows + static_cast<size_t>(bh) * args.S : nullptr;
+    const int* kv_rows = args.kv_rows ? args.kv_rows + static_cast<size_t>(bh) * args.S : nullptr;
+    auto dst_off = [&](int r) -> uint32_t {
+      return static_cast<uint32_t>((pl >> 3) * Cfg::kPanelBytes + r * 128 + (((pl & 7) ^ (r & 7)) << 4));
+    };
+    // Each producer warp owns the rows r with (r mod 6) in {2*pw, 2*pw+1}.  Lane L first resolves the source
+    // row of the warp's L-th row (all lanes in parallel: one window load of the run list + one optional
+    // index load), then the half-warps stream the rows, fetching each row's source with a shuffle.
+    auto my_row = [&](int L) -> int { return 6 * (L >> 1) + 2 * pw + (L & 1); };  // L-th row of this warp
+    // ---- Q (rows past nrows are zero-filled)
+    for (int base = 0; base < ntiles * kTileRows; base += 6 * 16) {  // 32 rows of this warp per pass
+      const int r_mine = base + my_row(lane);
+      long long src_mine = -1;
+      if (r_mine < nrows) {
+        const int qr = q_row0 + r_mine;
+        src_mine = q_rows ? __ldg(&q_rows[qr]) : qr;
+      }
+#pragma unroll 4
+      for (int k = 0; k < 16; ++k) {
+        const int L = 2 * k + (lane >> 4);
+        const int r = base + my_row(L);
+        const long long src = __shfl_sync(0xffffffffu, src_mine, L);
+        if (r < ntiles * kTileRows && lane_live)
+          cp_async16(sQ + (r >> 7) * Cfg::kTileBytes + dst_off(r & 127),
+                     qp + (src < 0 ? 0 : src) * args.in_row_stride + pl * 8, src >= 0 ? 16u : 0u);
+      }
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(smem_u32(&bars->q_full));
+    // ---- K(j), V(j): two ring slots per chunk, software-pipelined one chunk ahead (measured faster than
+    // hardware completion arrivals via cp.async.mbarrier.arrive.noinc, which let the producers run further
+    // ahead but lowered the achieved copy rate)
+    int pend_k = -1, pend_v = -1;
+    for (int j = 0; j < nchunks; ++j) {
+      const int it = 2 * j;
+      const int kslot = it % kStages, vslot = (it + 1) % kStages;
+      // resolve this warp's 42-44 rows of the chunk: position -> run (binary search in the shared-memory run
+      // table) -> source row (optional index vector)
+      long long src_a = -1, src_b = -1;  // lane L: rows my_row(L) and my_row(L + 32)
+      {
+        auto resolve = [&](int r) -> long long {
+          const int pos = j * kChunkCols + r;
+          if (r >= kChunkCols || pos >= total_kv) return -1;
+          int lo = 0, hi = nruns - 1;  // largest run with keys_before <= pos
+          while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (__ldg(&s_runs[mid].y) <= pos) lo = mid;
+            else hi = mid - 1;
+          }
+          const int2 rr = __ldg(&s_runs[lo]);
+          const int prow = rr.x + (pos - rr.y);
+          return kv_rows ? static_cast<long long>(__ldg(&kv_rows[prow])) : prow;
+        };
+        src_a = resolve(my_row(lane));
+        src_b = resolve(my_row(lane + 32));
+      }
+      mbar_wait(smem_u32(&bars->kv_empty[kslot]), ((it / kStages) & 1) ^ 1, 1);
+      mbar_wait(smem_u32(&bars->kv_empty[vslot]), (((it + 1) / kStages) & 1) ^ 1, 1);
+      const uint32_t kd = sRing + kslot * Cfg::kTileBytes, vd = sRing + vslot * Cfg::kTileBytes;
+#pragma unroll 4
+      for (int k = 0; k < 22; ++k) {
+        const int L = 2 * k + (lane >> 4);      // which of the warp's rows this half-warp copies now
+        const int r = my_row(L);
+        const long long sa = __shfl_sync(0xffffffffu, src_a, L & 31);
+        const long long sb = __shfl_sync(0xffffffffu, src_b, L & 31);
+        const long long src = L < 32 ? sa : sb;
+        if (r < kChunkCols && lane_live) {
+          const uint32_t off = dst_off(r);
+          const long long so = (src < 0 ? 0 : src) * args.in_row_stride + pl * 8;
+          cp_async16(kd + off, kp + so, src >= 0 ? 16u : 0u);
+          cp_async16(vd + off, vp + so, src >= 0 ? 16u : 0u);
+        }
+      }
+      cp_async_commit();
+      if (pend_k >= 0) {  // the previous chunk's group has landed once at most one group is pending
+        cp_async_wait<1>();
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(smem_u32(&bars->kv_full[pend_k]));
+          mbar_arrive(smem_u32(&bars->kv_full[pend_v]));
+        }
+      }
+      pend_k = kslot;
+      pend_v = vslot;
+    }
+    if (pend_k >= 0) {
+      cp_async_wait<0>();
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(smem_u32(&bars->kv_full[pend_k]));
+        mbar_arrive(smem_u32(&bars->kv_full[pend_v]));
+      }
+    }
+  } else if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     setmaxnreg_dec<kRegsLight>();
     if (lane == 0) {
@@ -117,8 +244,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
         const int kv0 = __ldg(&chunks[j].x);
 #pragma unroll
         for (int kv = 0; kv < 2; ++kv, ++it) {
-          const int slot = it % Cfg::kStages;
-          const uint32_t ph = (it / Cfg::kStages) & 1;
+          const int slot = it % kStages;
+          const uint32_t ph = (it / kStages) & 1;
           mbar_wait(smem_u32(&bars->kv_empty[slot]), ph ^ 1, 1);
           const uint32_t fb = smem_u32(&bars->kv_full[slot]);
           mbar_expect_tx(fb, Cfg::kTileBytes);
@@ -156,14 +283,21 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
           mma_ts(d_tmem, p_tmem + kk * 8, b, idesc, (acc || kk > 0) ? 1u : 0u);
         }
       };
-      auto round16 = [](int meta) { return (chunk_valid(meta) + 15) & ~15; };
+      // MMA N of chunk jj: run-tail / band chunks carry it in the chunk list; gather chunks are all full
+      // except the last
+      auto chunk_n = [&](int jj) -> int {
+        const int vld = gather ? min(kChunkCols, total_kv - jj * kChunkCols) : chunk_valid(__ldg(&chunks[jj].y));
+        return (vld + 15) & ~15;
+      };
 
       mbar_wait(smem_u32(&bars->q_full), 0, 2);
+      if constexpr (kGather) fence_proxy_async_smem();
       int ring = 0;
-      int n_cur = round16(__ldg(&chunks[0].y));
+      int n_cur = chunk_n(0);
       {
         const int slot = 0;
         mbar_wait(smem_u32(&bars->kv_full[slot]), 0, 3);
+        if constexpr (kGather) fence_proxy_async_smem();  // cp.async wrote through the generic proxy
         tc_fence_after();
         issue_qk(0, slot, n_cur);
         tc_commit(smem_u32(&bars->s_full[0]));
@@ -176,23 +310,25 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
       }
       for (int j = 0; j < nchunks; ++j) {
         const bool has_next = (j + 1 < nchunks);
-        const int vslot = ring % Cfg::kStages;
-        const uint32_t vph = (ring / Cfg::kStages) & 1;
+        const int vslot = ring % kStages;
+        const uint32_t vph = (ring / kStages) & 1;
         ++ring;
         int kslot = 0, n_next = 0;
         uint32_t kph = 0;
         if (has_next) {
-          kslot = ring % Cfg::kStages;
-          kph = (ring / Cfg::kStages) & 1;
+          kslot = ring % kStages;
+          kph = (ring / kStages) & 1;
           ++ring;
-          n_next = round16(__ldg(&chunks[j + 1].y));
+          n_next = chunk_n(j + 1);
         }
         mbar_wait(smem_u32(&bars->kv_full[vslot]), vph, 4);
+        if constexpr (kGather) fence_proxy_async_smem();
         mbar_wait(smem_u32(&bars->p_full[0]), j & 1, 5);
         tc_fence_after();
         issue_pv(0, vslot, n_cur, j > 0);
         if (has_next) {
           mbar_wait(smem_u32(&bars->kv_full[kslot]), kph, 6);
+          if constexpr (kGather) fence_proxy_async_smem();
           tc_fence_after();
           issue_qk(0, kslot, n_next);
           tc_commit(smem_u32(&bars->s_full[0]));
@@ -235,17 +371,17 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
 
       float m_used = -INFINITY;  // reference max the stored P / O are scaled against
       float l_run = 0.f;
-      int2 ch = nchunks > 0 ? __ldg(&chunks[0]) : make_int2(0, 0);
+      int2 ch = (nchunks > 0 && !gather) ? __ldg(&chunks[0]) : make_int2(0, 0);
       MaskRow mrow;
       mrow.init(mode, qm, m0, m1, m2);
 
       for (int j = 0; j < nchunks; ++j) {
         const int kv0 = ch.x;
-        const int valid = chunk_valid(ch.y);
-        const bool elem = (ch.y & kChunkElem) != 0;
+        const int valid = gather ? min(kChunkCols, total_kv - j * kChunkCols) : chunk_valid(ch.y);
+        const bool elem = !gather && (ch.y & kChunkElem) != 0;
         const int ncols = (valid + 15) & ~15;
         const int ngroups = (ncols + 31) >> 5;
-        if (j + 1 < nchunks) ch = __ldg(&chunks[j + 1]);
+        if (!gather && j + 1 < nchunks) ch = __ldg(&chunks[j + 1]);
 
         mbar_wait(sbar, j & 1, 8 + t);
         tc_fence_after();

@@ -94,6 +94,27 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, uint
 }
 
 // ---------------------------------------------------------------------------------------------
+// cp.async (LDGSTS) row gathers: 16-byte pieces, L2-only caching, zero fill when src_bytes == 0
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+// the mbarrier receives one arrival from this thread once all of the thread's earlier cp.async copies have
+// landed (.noinc: the arrival is part of the barrier's expected count)
+__device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+// make generic-proxy smem writes (cp.async, st.shared) visible to the async proxy (tcgen05.mma / TMA)
+__device__ __forceinline__ void fence_proxy_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
 // tcgen05: TMEM allocation
 // ---------------------------------------------------------------------------------------------
 template <uint32_t kCols>

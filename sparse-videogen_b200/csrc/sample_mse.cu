@@ -189,6 +189,11 @@ int svgb_sample_mse(const void* q, const void* k, const void* v, const int32_t* 
     a.m2 = thres;
     a.q_index = reinterpret_cast<const int*>(w + L.qidx);
     a.out_f32 = 1;
+    a.gather = 0;
+    a.item_total = nullptr;
+    a.q_rows = a.kv_rows = nullptr;
+    a.q_ptr = a.k_ptr = a.v_ptr = nullptr;
+    a.in_row_stride = a.in_head_stride = 0;
     if (attn_fwd_impl(w + L.qg, rows_per_head, D, static_cast<long long>(rows_per_head) * D, k, v, S, D,
                       static_cast<long long>(S) * D, dtype, BH, D, a, L.nsplit, st))
       return -1;

@@ -24,7 +24,7 @@ class Plan(C.Structure):
         ("items_stride", C.c_int32), ("counts_stride", C.c_int32),
         ("mask_mode", C.c_int32), ("m0", C.c_int32), ("m1", C.c_int32), ("m2", C.c_int32),
         ("counts_off", C.c_int64), ("items_off", C.c_int64), ("chunks_off", C.c_int64),
-        ("bytes", C.c_int64),
+        ("bytes", C.c_int64), ("aux_off", C.c_int64),
     ]
 
 
@@ -38,9 +38,11 @@ _PROTOS = {
     "svgb_device_check": [C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)],
     "svgb_attn_plan_varblock_bytes": [_i, _i, _i, _i, _psz],
     "svgb_attn_plan_varblock": [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _sz, _pplan, _vp],
+    "svgb_attn_plan_varblock_gather": [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _sz, _pplan, _vp],
     "svgb_attn_plan_band_bytes": [_i, _psz],
     "svgb_attn_plan_band": [_i, _i, _i, _i, _i, _i, _vp, _sz, _pplan, _vp],
     "svgb_attn_fwd": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _ll, _ll, _ll, _ll, _f, _pplan, _vp, _vp],
+    "svgb_attn_fwd_gather": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _ll, _ll, _ll, _ll, _f, _pplan, _vp, _vp],
     "svgb_density": [_vp, _vp, _vp, _i, _i, _i, _vp, _vp],
     "svgb_argsort_labels_bytes": [_i, _i, _i, _psz],
     "svgb_argsort_labels": [_vp, _i, _i, _i, _vp, _vp, _vp, _sz, _vp],

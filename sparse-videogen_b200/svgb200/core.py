@@ -78,8 +78,10 @@ class AttnPlan:
 
 
 def plan_varblock(block_map: torch.Tensor, row_sz: torch.Tensor, col_sz: torch.Tensor, S: int,
-                  ws: Optional[torch.Tensor] = None) -> AttnPlan:
-    """block_map [BH,QC,KC] bool/uint8, row_sz [BH,QC], col_sz [BH,KC] (any int dtype) on GPU."""
+                  ws: Optional[torch.Tensor] = None, gather: bool = False) -> AttnPlan:
+    """block_map [BH,QC,KC] bool/uint8, row_sz [BH,QC], col_sz [BH,KC] (any int dtype) on GPU.
+    gather=True lowers the map for the row-gather kernel path (exactly-full chunks, optional fused
+    permutation through attn_fwd(..., q_rows=, kv_rows=))."""
     _need_cuda(block_map, row_sz, col_sz)
     BH, QC, KC = block_map.shape
     m = block_map.contiguous()
@@ -91,9 +93,9 @@ def plan_varblock(block_map: torch.Tensor, row_sz: torch.Tensor, col_sz: torch.T
     if ws is None:
         ws = workspace(("vb", BH, S, QC, KC), nbytes.value, m.device)
     desc = Plan()
-    check(lib().svgb_attn_plan_varblock(m.data_ptr(), r.data_ptr(), c.data_ptr(), BH, S, QC, KC,
-                                        ws.data_ptr(), ws.numel(), C.byref(desc), _stream(m)),
-          "svgb_attn_plan_varblock")
+    fn = lib().svgb_attn_plan_varblock_gather if gather else lib().svgb_attn_plan_varblock
+    check(fn(m.data_ptr(), r.data_ptr(), c.data_ptr(), BH, S, QC, KC, ws.data_ptr(), ws.numel(), C.byref(desc),
+             _stream(m)), "svgb_attn_plan_varblock")
     _bump()
     return AttnPlan(desc, ws)
 
@@ -114,6 +116,7 @@ def plan_band(mask_mode: int, m0: int, m1: int, m2: int, BH: int, S: int, device
 # attention
 # ----------------------------------------------------------------------------------------------
 def attn_fwd(q, k, v, plan: AttnPlan, *, layout: str = "bhsd", o_rows: Optional[torch.Tensor] = None,
+             q_rows: Optional[torch.Tensor] = None, kv_rows: Optional[torch.Tensor] = None,
              return_lse: bool = False, sm_scale: Optional[float] = None, out: Optional[torch.Tensor] = None):
     """layout 'bhsd': q,k,v [B,H,S,D] contiguous;  'shd': [S,H,D] contiguous (ops API)."""
     _need_cuda(q, k, v)
@@ -134,9 +137,21 @@ def attn_fwd(q, k, v, plan: AttnPlan, *, layout: str = "bhsd", o_rows: Optional[
     if o_rows is not None:
         o_rows = o_rows.reshape(BH, S).to(torch.int32).contiguous()
     scale = float(D) ** -0.5 if sm_scale is None else float(sm_scale)
-    check(lib().svgb_attn_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), _p(lse), _p(o_rows),
-                              _dt(q), BH, S, D, rs, hs, rs, hs, scale, C.byref(plan.desc),
-                              plan.ws.data_ptr(), _stream(q)), "svgb_attn_fwd")
+    if plan.desc.kind == 3:
+        if q_rows is not None:
+            q_rows = q_rows.reshape(BH, S).to(torch.int32).contiguous()
+        if kv_rows is not None:
+            kv_rows = kv_rows.reshape(BH, S).to(torch.int32).contiguous()
+        check(lib().svgb_attn_fwd_gather(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), _p(lse),
+                                         _p(q_rows), _p(kv_rows), _p(o_rows), _dt(q), BH, S, D, rs, hs, rs, hs,
+                                         scale, C.byref(plan.desc), plan.ws.data_ptr(), _stream(q)),
+              "svgb_attn_fwd_gather")
+    else:
+        if q_rows is not None or kv_rows is not None:
+            raise SvgbError("q_rows / kv_rows need a gather plan (plan_varblock(..., gather=True))")
+        check(lib().svgb_attn_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), _p(lse), _p(o_rows),
+                                  _dt(q), BH, S, D, rs, hs, rs, hs, scale, C.byref(plan.desc),
+                                  plan.ws.data_ptr(), _stream(q)), "svgb_attn_fwd")
     _bump()
     return (o, lse) if return_lse else o
 

@@ -51,7 +51,7 @@ def test_argument_errors_are_reported(lib):
 def test_plan_struct_layout_matches_header():
     from svgb200._lib import Plan
 
-    assert C.sizeof(Plan) == 10 * 4 + 4 * 8
+    assert C.sizeof(Plan) == 10 * 4 + 5 * 8
     assert Plan.counts_off.offset == 40
 
 

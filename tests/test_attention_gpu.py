@@ -40,7 +40,7 @@ def test_selftest_tile(cuda, D, dtype):
     torch.testing.assert_close(o.cpu(), o_ref, rtol=1e-3, atol=2e-2)
 
 
-def _run_varblock(cuda, H, D, S, MB, NB, density, dtype, seed, uniform_sizes=False):
+def _run_varblock(cuda, H, D, S, MB, NB, density, dtype, seed, uniform_sizes=False, gather=False):
     from oracle.attention import dynamic_block_sparse_fwd
     from svgb200 import core
 
@@ -55,7 +55,7 @@ def _run_varblock(cuda, H, D, S, MB, NB, density, dtype, seed, uniform_sizes=Fal
     q = torch.randn(1, H, S, D, generator=g).to(dtype)
     k = torch.randn(1, H, S, D, generator=g).to(dtype)
     v = torch.randn(1, H, S, D, generator=g).to(dtype)
-    plan = core.plan_varblock(bmap.to(cuda), row.to(cuda), col.to(cuda), S)
+    plan = core.plan_varblock(bmap.to(cuda), row.to(cuda), col.to(cuda), S, gather=gather)
     o = core.attn_fwd(q.to(cuda), k.to(cuda), v.to(cuda), plan)
     torch.cuda.synchronize()
     ref = dynamic_block_sparse_fwd(q, k, v, bmap[None], row[None], col[None])
@@ -71,6 +71,43 @@ def test_variable_block_sparse_attention(cuda, D, S, MB, NB, density, dtype):
     """Reference grid of test_sparse_attn_dyn_blk_wan.py (heads folded to 2 per case)."""
     o, ref = _run_varblock(cuda, 2, D, S, MB, NB, density, dtype, seed=hash((D, S, MB, NB)) % 1000)
     torch.testing.assert_close(o, ref, atol=1e-2, rtol=1e-2)
+
+
+@pytest.mark.parametrize("D", [128, 64])
+@pytest.mark.parametrize("S,MB,NB", [(256, 10, 50), (4096, 20, 100), (1000, 7, 33)])
+@pytest.mark.parametrize("density", [0.2, 0.7])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_variable_block_gather_path(cuda, D, S, MB, NB, density, dtype):
+    """Same grid through the row-gather kernel path (cp.async producers, exactly-full chunks)."""
+    o, ref = _run_varblock(cuda, 2, D, S, MB, NB, density, dtype, seed=hash((D, S, MB)) % 1000, gather=True)
+    torch.testing.assert_close(o, ref, atol=1e-2, rtol=1e-2)
+
+
+def test_gather_path_fused_permutation(cuda):
+    """q_rows / kv_rows / o_rows = cluster argsorts: SVG2 attention straight on the un-permuted tensors equals
+    masked attention under  allowed(i, j) = map[qlabel(i), klabel(j)]  (and equals the permute->attend->
+    inverse-permute pipeline of hyvideo/attention.py:628-655,778-783)."""
+    from svgb200 import core
+
+    g = torch.Generator().manual_seed(21)
+    H, S, D, QC, KC = 3, 1500, 128, 9, 31
+    q, k, v = (torch.randn(1, H, S, D, generator=g).to(torch.bfloat16) for _ in range(3))
+    ql = torch.randint(0, QC, (H, S), generator=g)
+    kl = torch.randint(0, KC, (H, S), generator=g)
+    kl[0][kl[0] == 3] = 4  # an empty key cluster
+    bm = torch.rand(H, QC, KC, generator=g) > 0.5
+    bm[1, 2, :] = False     # a query cluster that sees nothing
+    qperm, qcnt = core.argsort_labels(ql.to(cuda), QC)
+    kperm, kcnt = core.argsort_labels(kl.to(cuda), KC)
+    plan = core.plan_varblock(bm.to(cuda), qcnt, kcnt, S, gather=True)
+    o = core.attn_fwd(q.to(cuda), k.to(cuda), v.to(cuda), plan, q_rows=qperm, kv_rows=kperm, o_rows=qperm)
+    o = o.float().cpu()
+    for h in range(H):
+        allowed = bm[h][ql[h]][:, kl[h]]
+        s = (q[0, h].float() @ k[0, h].float().T) * D ** -0.5
+        w = torch.nan_to_num(torch.softmax(s.masked_fill(~allowed, float("-inf")), -1), nan=0.0)
+        torch.testing.assert_close(o[0, h], w @ v[0, h].float(), atol=1e-2, rtol=1e-2)
+    assert torch.all(o[0, 1][ql[1] == 2] == 0)
 
 
 def test_variable_block_long_uniform(cuda):
