@@ -27,6 +27,7 @@ extern "C" {
 
 #define SVGB_BF16 0
 #define SVGB_F16 1
+#define SVGB_E4M3 2 /* fp8 e4m3 inputs (svgb_attn_fwd_fp8 only) */
 
 /* element-mask families for the SVG1 band plan (reference generate_temporal_head_mask_mod) */
 #define SVGB_MASK_NONE 0
@@ -108,6 +109,18 @@ int svgb_attn_fwd_gather(const void* q, const void* k, const void* v, void* o, f
                          int BH, int S, int D, long long row_stride, long long head_stride,
                          long long o_row_stride, long long o_head_stride, float sm_scale,
                          const svgb_plan* plan, const void* plan_ws, void* stream);
+
+/* FP8 attention (BASELINE config 5; the reference has no FP8 sparse attention, README.md:117).  q8,k8,v8 are
+ * e4m3 bytes [BH,S,D] (D = 128) with per-head dequantisation scales (x ~= x8 * scale[h]); QK^T and PV run as
+ * tcgen05 kind::f8f6f4 MMAs, P is quantised to e4m3 in TMEM with its range kept in (0, 2^8] (offset 2^4 + lazy-rescale slack 2^4), the output is
+ * bf16.  Any plan kind except the row-gather one.  svgb_quantize_e4m3 produces the inputs: per-head absmax
+ * scaling (scale = absmax / 448), round-to-nearest, saturating. */
+int svgb_quantize_e4m3(const void* x, int dtype, void* x8, float* scale, int BH, int S, int D, void* stream);
+int svgb_attn_fwd_fp8(const void* q8, const void* k8, const void* v8, const float* q_scale, const float* k_scale,
+                      const float* v_scale, void* o, float* lse, const int32_t* o_rows, int BH, int S, int D,
+                      long long row_stride, long long head_stride, long long o_row_stride,
+                      long long o_head_stride, float sm_scale, const svgb_plan* plan, const void* plan_ws,
+                      void* stream);
 
 /* density of a variable-block map (density_calculation, svg/kmeans_utils.py:13-31) -> float [BH] */
 int svgb_density(const uint8_t* map, const int32_t* row_sz, const int32_t* col_sz, int BH, int QC,

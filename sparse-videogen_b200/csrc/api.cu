@@ -37,16 +37,18 @@ int encode_tmap_hsd(CUtensorMap* map, const void* base, int dtype, int BH, int S
   PFN_encodeTiled enc = get_encode();
   SVGB_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
   SVGB_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "tensor base must be 16-byte aligned");
-  SVGB_REQUIRE(row_stride_elems % 8 == 0 && head_stride_elems % 8 == 0,
-               "strides must be multiples of 8 elements (16 bytes)");
   cuuint64_t dims[3] = {static_cast<cuuint64_t>(D), static_cast<cuuint64_t>(S),
                         static_cast<cuuint64_t>(BH)};
-  cuuint64_t strides[2] = {static_cast<cuuint64_t>(row_stride_elems) * 2,
-                           static_cast<cuuint64_t>(head_stride_elems) * 2};
-  cuuint32_t box[3] = {64, static_cast<cuuint32_t>(box_rows), 1};
+  const int eb = dtype == SVGB_E4M3 ? 1 : 2;  // bytes per element
+  SVGB_REQUIRE((row_stride_elems * eb) % 16 == 0 && (head_stride_elems * eb) % 16 == 0,
+               "strides must be multiples of 16 bytes");
+  cuuint64_t strides[2] = {static_cast<cuuint64_t>(row_stride_elems) * eb,
+                           static_cast<cuuint64_t>(head_stride_elems) * eb};
+  cuuint32_t box[3] = {static_cast<cuuint32_t>(128 / eb), static_cast<cuuint32_t>(box_rows), 1};  // 128-byte rows
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(map, dtype == SVGB_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
-                                           : CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
+                        : dtype == SVGB_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16
+                                            : CU_TENSOR_MAP_DATA_TYPE_UINT8,
                    3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

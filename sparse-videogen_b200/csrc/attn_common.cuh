@@ -143,6 +143,11 @@ struct AttnArgs {
   int mask_mode, m0, m1, m2;
   const int* q_index;       // optional [S]: query position used by the element mask (sampled rows)
   int out_f32;              // 1: o is fp32 (used for split-KV partials)
+  // FP8 (e4m3) inputs: per-head dequantisation scales [BH]; s_q * s_k multiplies the logits, s_v the
+  // output.  NULL for 16-bit inputs.
+  const float* q_scale;
+  const float* k_scale;
+  const float* v_scale;
   // ---- gather mode (SVG2): `chunks` holds RUNS {src_start, cum_before} (+ a sentinel {0, total}) of the
   // selected key ranges; K/V rows are gathered with cp.async into exactly-full 128-token chunks, optionally
   // through row-index vectors so the cluster permutation of Q, K, V never materialises in HBM.

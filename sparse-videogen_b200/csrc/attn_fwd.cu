@@ -312,16 +312,21 @@ selftest_tile_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_cons
   }
 }
 
-template <int D, bool BF16>
+template <int D, int DT>
 static int launch_attn(const CUtensorMap& qm, const CUtensorMap& km, const CUtensorMap& vm,
                        const AttnArgs& args, dim3 grid, cudaStream_t stream) {
-  using Cfg = AttnCfg<D>;
-  if (args.gather) {
-    auto kern = attn_fwd_kernel<D, BF16, true>;
-    SVGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    kern<<<grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(qm, km, vm, args);
-  } else {
-    auto kern = attn_fwd_kernel<D, BF16, false>;
+  using Cfg = AttnCfg<D, DT>;
+  if constexpr (DT != DT_E4M3) {
+    if (args.gather) {
+      auto kern = attn_fwd_kernel<D, DT, true>;
+      SVGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+      kern<<<grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(qm, km, vm, args);
+      SVGB_LAUNCH_OK();
+      return 0;
+    }
+  }
+  {
+    auto kern = attn_fwd_kernel<D, DT, false>;
     SVGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     kern<<<grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(qm, km, vm, args);
   }
@@ -345,18 +350,22 @@ int attn_fwd_impl(const void* q, int Sq, long long q_rs, long long q_hs, const v
                   long long kv_rs, long long kv_hs, int dtype, int BH, int D, const AttnArgs& a, int grid_x,
                   cudaStream_t st) {
   SVGB_REQUIRE(D == 64 || D == 128, "head_dim %d unsupported (64 or 128)", D);
-  SVGB_REQUIRE(dtype == SVGB_BF16 || dtype == SVGB_F16, "dtype %d unsupported", dtype);
+  SVGB_REQUIRE(dtype == SVGB_BF16 || dtype == SVGB_F16 || dtype == SVGB_E4M3, "dtype %d unsupported", dtype);
   CUtensorMap qm, km, vm;
   if (encode_tmap_hsd(&qm, q, dtype, BH, Sq, D, q_rs, q_hs)) return -1;
   if (encode_tmap_hsd(&km, k, dtype, BH, Skv, D, kv_rs, kv_hs)) return -1;
   if (encode_tmap_hsd(&vm, v, dtype, BH, Skv, D, kv_rs, kv_hs)) return -1;
   dim3 grid(grid_x, BH);
-  if (D == 128) {
-    return dtype == SVGB_BF16 ? launch_attn<128, true>(qm, km, vm, a, grid, st)
-                              : launch_attn<128, false>(qm, km, vm, a, grid, st);
+  if (dtype == SVGB_E4M3) {
+    SVGB_REQUIRE(D == 128 && !a.gather, "the e4m3 path needs head_dim 128 and a non-gather plan");
+    return launch_attn<128, DT_E4M3>(qm, km, vm, a, grid, st);
   }
-  return dtype == SVGB_BF16 ? launch_attn<64, true>(qm, km, vm, a, grid, st)
-                            : launch_attn<64, false>(qm, km, vm, a, grid, st);
+  if (D == 128) {
+    return dtype == SVGB_BF16 ? launch_attn<128, DT_BF16>(qm, km, vm, a, grid, st)
+                              : launch_attn<128, DT_F16>(qm, km, vm, a, grid, st);
+  }
+  return dtype == SVGB_BF16 ? launch_attn<64, DT_BF16>(qm, km, vm, a, grid, st)
+                            : launch_attn<64, DT_F16>(qm, km, vm, a, grid, st);
 }
 
 static int varblock_chunk_cap(int S, int KC) { return S / kChunkCols + (KC + 1) / 2 + 2; }
@@ -470,14 +479,15 @@ int svgb_attn_plan_band(int mask_mode, int m0, int m1, int m2, int BH, int S, vo
   return 0;
 }
 
-static int attn_fwd_entry(const void* q, const void* k, const void* v, void* o, float* lse,
+static int attn_fwd_entry(const void* q, const void* k, const void* v, const float* q_scale, const float* k_scale,
+                          const float* v_scale, void* o, float* lse,
                           const int32_t* q_rows, const int32_t* kv_rows, const int32_t* o_rows, int dtype, int BH,
                           int S, int D, long long row_stride, long long head_stride, long long o_row_stride,
                           long long o_head_stride, float sm_scale, const svgb_plan* plan, const void* plan_ws,
                           void* stream) {
   SVGB_REQUIRE(q && k && v && o && plan && plan_ws, "null pointer");
   SVGB_REQUIRE(D == 64 || D == 128, "head_dim %d unsupported (64 or 128)", D);
-  SVGB_REQUIRE(dtype == SVGB_BF16 || dtype == SVGB_F16, "dtype %d unsupported", dtype);
+  SVGB_REQUIRE(dtype == SVGB_BF16 || dtype == SVGB_F16 || dtype == SVGB_E4M3, "dtype %d unsupported", dtype);
   SVGB_REQUIRE(plan->S == S && (plan->items_stride == 0 || plan->BH == BH),
                "plan was built for BH=%d S=%d, called with BH=%d S=%d", plan->BH, plan->S, BH, S);
   SVGB_REQUIRE((reinterpret_cast<uintptr_t>(o) & 15) == 0 && o_row_stride % 8 == 0 && o_head_stride % 8 == 0,
@@ -504,6 +514,9 @@ static int attn_fwd_entry(const void* q, const void* k, const void* v, void* o, 
   a.m2 = plan->m2;
   a.q_index = nullptr;
   a.out_f32 = 0;
+  a.q_scale = q_scale;
+  a.k_scale = k_scale;
+  a.v_scale = v_scale;
   a.gather = plan->kind == 3 ? 1 : 0;
   a.item_total = plan->kind == 3 ? reinterpret_cast<const int*>(ws + plan->aux_off) : nullptr;
   a.q_rows = q_rows;
@@ -521,8 +534,18 @@ int svgb_attn_fwd(const void* q, const void* k, const void* v, void* o, float* l
                   const int32_t* o_rows, int dtype, int BH, int S, int D, long long row_stride,
                   long long head_stride, long long o_row_stride, long long o_head_stride,
                   float sm_scale, const svgb_plan* plan, const void* plan_ws, void* stream) {
-  return attn_fwd_entry(q, k, v, o, lse, nullptr, nullptr, o_rows, dtype, BH, S, D, row_stride, head_stride,
-                        o_row_stride, o_head_stride, sm_scale, plan, plan_ws, stream);
+  return attn_fwd_entry(q, k, v, nullptr, nullptr, nullptr, o, lse, nullptr, nullptr, o_rows, dtype, BH, S, D,
+                        row_stride, head_stride, o_row_stride, o_head_stride, sm_scale, plan, plan_ws, stream);
+}
+
+int svgb_attn_fwd_fp8(const void* q8, const void* k8, const void* v8, const float* q_scale, const float* k_scale,
+                      const float* v_scale, void* o, float* lse, const int32_t* o_rows, int BH, int S, int D,
+                      long long row_stride, long long head_stride, long long o_row_stride,
+                      long long o_head_stride, float sm_scale, const svgb_plan* plan, const void* plan_ws,
+                      void* stream) {
+  SVGB_REQUIRE(q_scale && k_scale && v_scale, "fp8 attention needs the three per-head scale vectors");
+  return attn_fwd_entry(q8, k8, v8, q_scale, k_scale, v_scale, o, lse, nullptr, nullptr, o_rows, SVGB_E4M3, BH, S,
+                        D, row_stride, head_stride, o_row_stride, o_head_stride, sm_scale, plan, plan_ws, stream);
 }
 
 int svgb_attn_fwd_gather(const void* q, const void* k, const void* v, void* o, float* lse, const int32_t* q_rows,
@@ -530,8 +553,8 @@ int svgb_attn_fwd_gather(const void* q, const void* k, const void* v, void* o, f
                          long long row_stride, long long head_stride, long long o_row_stride,
                          long long o_head_stride, float sm_scale, const svgb_plan* plan, const void* plan_ws,
                          void* stream) {
-  return attn_fwd_entry(q, k, v, o, lse, q_rows, kv_rows, o_rows, dtype, BH, S, D, row_stride, head_stride,
-                        o_row_stride, o_head_stride, sm_scale, plan, plan_ws, stream);
+  return attn_fwd_entry(q, k, v, nullptr, nullptr, nullptr, o, lse, q_rows, kv_rows, o_rows, dtype, BH, S, D,
+                        row_stride, head_stride, o_row_stride, o_head_stride, sm_scale, plan, plan_ws, stream);
 }
 
 int svgb_density(const uint8_t* map, const int32_t* row_sz, const int32_t* col_sz, int BH, int QC,

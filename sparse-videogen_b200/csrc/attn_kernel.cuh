@@ -24,13 +24,21 @@
 
 namespace svgb {
 
-template <int D>
+// element type of Q/K/V (and of P): 0 = bf16, 1 = fp16, 2 = fp8 e4m3 (output bf16)
+constexpr int DT_BF16 = 0, DT_F16 = 1, DT_E4M3 = 2;
+
+template <int D, int DT = DT_BF16>
 struct AttnCfg {
   static_assert(D == 64 || D == 128, "head_dim must be 64 or 128");
-  static constexpr int kHalves = D / 64;                 // 64-column (128-byte) swizzle panels
+  static_assert(DT != DT_E4M3 || D == 128, "the e4m3 path is built for head_dim 128 (128-byte rows)");
+  static constexpr int kElemBytes = DT == DT_E4M3 ? 1 : 2;
+  static constexpr int kRowBytes = D * kElemBytes;
+  static constexpr int kHalves = kRowBytes / 128;        // 128-byte swizzle panels per row
+  static constexpr int kPanelElems = 128 / kElemBytes;   // elements per panel row (TMA box width)
+  static constexpr int kMmaK = 32 / kElemBytes;          // K elements per tcgen05.mma (32 bytes)
   static constexpr int kPanelBytes = 128 * 128;          // 128 rows x 128 B
   static constexpr int kTileBytes = kPanelBytes * kHalves;
-  static constexpr int kStages = (D == 128) ? 5 : 8;
+  static constexpr int kStages = (kRowBytes == 256) ? 5 : 8;
   // gather instantiation: one stage less; the freed tile holds the item's run table in shared memory
   static constexpr int kStagesGather = kStages;
   static constexpr int kMaxRunsSmem = kTileBytes / 8 - 1;
@@ -60,11 +68,14 @@ constexpr int kRegsSoftmax = 224;
 
 // kGather selects the producer: false = TMA boxes over contiguous key ranges (chunk list), true = cp.async
 // row gathers over a run list (separate instantiations keep each one's register footprint small).
-template <int D, bool BF16, bool kGather>
+template <int D, int DT, bool kGather>
 __global__ void __launch_bounds__(384, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant__ CUtensorMap kmap,
                 const __grid_constant__ CUtensorMap vmap, const AttnArgs args) {
-  using Cfg = AttnCfg<D>;
+  using Cfg = AttnCfg<D, DT>;
+  constexpr bool BF16 = DT != DT_F16;  // output / 16-bit P format (fp8 inputs produce bf16 output)
+  constexpr bool FP8 = DT == DT_E4M3;
+  static_assert(!(FP8 && kGather), "row-gather producers are 16-bit only");
   const int bh = blockIdx.y;
   const int n_items = args.item_count[bh * args.counts_stride];
   if (static_cast<int>(blockIdx.x) >= n_items) return;
@@ -237,7 +248,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
       mbar_expect_tx(qbar, ntiles * Cfg::kTileBytes);
       for (int t = 0; t < ntiles; ++t)
         for (int h = 0; h < Cfg::kHalves; ++h)
-          tma_load_3d(sQ + t * Cfg::kTileBytes + h * Cfg::kPanelBytes, &qmap, qbar, h * 64,
+          tma_load_3d(sQ + t * Cfg::kTileBytes + h * Cfg::kPanelBytes, &qmap, qbar, h * Cfg::kPanelElems,
                       q_row0 + t * kTileRows, bh);
       int it = 0;
       for (int j = 0; j < nchunks; ++j) {
@@ -251,7 +262,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
           mbar_expect_tx(fb, Cfg::kTileBytes);
           const CUtensorMap* map = kv == 0 ? &kmap : &vmap;
           for (int h = 0; h < Cfg::kHalves; ++h)
-            tma_load_3d(sRing + slot * Cfg::kTileBytes + h * Cfg::kPanelBytes, map, fb, h * 64, kv0,
+            tma_load_3d(sRing + slot * Cfg::kTileBytes + h * Cfg::kPanelBytes, map, fb, h * Cfg::kPanelElems, kv0,
                         bh);
         }
       }
@@ -261,33 +272,35 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
     setmaxnreg_dec<kRegsLight>();
     if (lane == 0 && nchunks > 0) {
       auto issue_qk = [&](int t, int slot, int ncols) {
-        const uint32_t idesc = make_idesc(128, ncols, BF16, false, false);
+        const uint32_t idesc = FP8 ? make_idesc_e4m3(128, ncols, false, false)
+                                   : make_idesc(128, ncols, DT == DT_BF16, false, false);
         const uint32_t d_tmem = tmem + (t == 0 ? Cfg::kSCol0 : Cfg::kSCol1);
 #pragma unroll
-        for (int kk = 0; kk < D / 16; ++kk) {
+        for (int kk = 0; kk < Cfg::kRowBytes / 32; ++kk) {  // 32 bytes of the head dim per MMA
           const uint32_t off = (kk >> 2) * Cfg::kPanelBytes + (kk & 3) * 32;
           const uint64_t a = desc_kmajor_sw128(sQ + t * Cfg::kTileBytes + off);
           const uint64_t b = desc_kmajor_sw128(sRing + slot * Cfg::kTileBytes + off);
-          mma_ss(d_tmem, a, b, idesc, kk > 0 ? 1u : 0u);
+          if constexpr (FP8) mma_ss_f8(d_tmem, a, b, idesc, kk > 0 ? 1u : 0u);
+          else mma_ss(d_tmem, a, b, idesc, kk > 0 ? 1u : 0u);
         }
       };
       auto issue_pv = [&](int t, int slot, int ncols, bool acc) {
-        const uint32_t idesc = make_idesc(128, D, BF16, false, true);
+        const uint32_t idesc = FP8 ? make_idesc_e4m3(128, D, false, true) : make_idesc(128, D, DT == DT_BF16, false, true);
         const uint32_t d_tmem = tmem + (t == 0 ? Cfg::kOCol0 : Cfg::kOCol1);
         const uint32_t p_tmem = tmem + (t == 0 ? Cfg::kSCol0 : Cfg::kSCol1);
-        const int nk = ncols >> 4;
+        const int nk = ncols / Cfg::kMmaK;
         for (int kk = 0; kk < nk; ++kk) {
-          // 16 kv rows per MMA: 16 x 128 B = 2048 B down the V panel; P advances 8 TMEM columns.
-          const uint64_t b =
-              desc_mnmajor_sw128(sRing + slot * Cfg::kTileBytes + kk * 2048, Cfg::kPanelBytes);
-          mma_ts(d_tmem, p_tmem + kk * 8, b, idesc, (acc || kk > 0) ? 1u : 0u);
+          // kMmaK kv rows per MMA: kMmaK x 128 B down the V panel; P advances 8 TMEM columns (32 bytes).
+          const uint64_t b = desc_mnmajor_sw128(sRing + slot * Cfg::kTileBytes + kk * Cfg::kMmaK * 128, Cfg::kPanelBytes);
+          if constexpr (FP8) mma_ts_f8(d_tmem, p_tmem + kk * 8, b, idesc, (acc || kk > 0) ? 1u : 0u);
+          else mma_ts(d_tmem, p_tmem + kk * 8, b, idesc, (acc || kk > 0) ? 1u : 0u);
         }
       };
       // MMA N of chunk jj: run-tail / band chunks carry it in the chunk list; gather chunks are all full
       // except the last
       auto chunk_n = [&](int jj) -> int {
         const int vld = gather ? min(kChunkCols, total_kv - jj * kChunkCols) : chunk_valid(__ldg(&chunks[jj].y));
-        return (vld + 15) & ~15;
+        return (vld + Cfg::kMmaK - 1) & ~(Cfg::kMmaK - 1);
       };
 
       mbar_wait(smem_u32(&bars->q_full), 0, 2);
@@ -364,7 +377,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
       const uint32_t lane_addr = tmem + (static_cast<uint32_t>(wq * 32) << 16);
       const uint32_t s_addr = lane_addr + (t == 0 ? Cfg::kSCol0 : Cfg::kSCol1);
       const uint32_t o_addr = lane_addr + (t == 0 ? Cfg::kOCol0 : Cfg::kOCol1);
-      const float c = args.scale_log2;
+      // fp8: logits carry s_q * s_k; P = 2^(x - m + 4) with the lazy-rescale slack at 4 keeps P in (0, 2^8]
+      // (e4m3 max 448) while the fresh-max case still has 13 binades below it
+      const float c = args.scale_log2 * (args.q_scale ? __ldg(&args.q_scale[bh]) * __ldg(&args.k_scale[bh]) : 1.f);
+      constexpr float kTau = FP8 ? 4.f : kRescaleTau;
+      constexpr float kPOff = FP8 ? 4.f : 0.f;
       const int mode = args.mask_mode, m0 = args.m0, m1 = args.m1, m2 = args.m2;
       const uint32_t sbar = smem_u32(&bars->s_full[t]);
       const uint32_t pbar = smem_u32(&bars->p_full[t]);
@@ -379,7 +396,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
         const int kv0 = ch.x;
         const int valid = gather ? min(kChunkCols, total_kv - j * kChunkCols) : chunk_valid(ch.y);
         const bool elem = !gather && (ch.y & kChunkElem) != 0;
-        const int ncols = (valid + 15) & ~15;
+        const int ncols = (valid + Cfg::kMmaK - 1) & ~(Cfg::kMmaK - 1);
         const int ngroups = (ncols + 31) >> 5;
         if (!gather && j + 1 < nchunks) ch = __ldg(&chunks[j + 1]);
 
@@ -426,7 +443,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
           const float m_new = fmaxf(m_used, mx);
           // lazy rescale: keep the stale reference max unless it grew by more than tau (log2 units)
           float alpha = 1.f;
-          if ((m_new - m_used) * c > kRescaleTau) {  // false when both are -inf (NaN compare)
+          if ((m_new - m_used) * c > kTau) {  // false when both are -inf (NaN compare)
             alpha = ex2_approx((m_used - m_new) * c);  // 0 when m_used == -inf
             m_used = m_new;
           }
@@ -443,7 +460,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
             }
           }
           l_run *= alpha;
-          const float mc = (m_used == -INFINITY) ? 0.f : m_used * c;
+          const float mc = (m_used == -INFINITY) ? 0.f : m_used * c - kPOff;
           const uint64_t c2 = pack_f32x2(c, c), nmc2 = pack_f32x2(-mc, -mc);
           uint64_t sum2 = pack_f32x2(0.f, 0.f);
           // P = exp2(S*c - m*c) -> 16-bit, packed two per TMEM column over the first half of the S tile.
@@ -453,6 +470,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
               if (g >= ngroups) return;
             }
             uint32_t pk[16];
+            float rs_hi[FP8 ? 16 : 1];
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
               const uint64_t x2 =
@@ -467,9 +485,22 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
                 p1 = ex2_approx(x1);
               }
               sum2 = fadd2(sum2, pack_f32x2(p0, p1));
-              pk[i] = pack2<BF16>(p0, p1);
+              if constexpr (FP8) {  // keep the fp32 pair; four of them make one e4m3x4 word below
+                pk[i] = __float_as_uint(p0);
+                rs_hi[i] = p1;
+              } else {
+                pk[i] = pack2<BF16>(p0, p1);
+              }
             }
-            tmem_st16(s_addr + g * 16, pk);
+            if constexpr (FP8) {
+              uint32_t p8[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                p8[i] = pack4_e4m3(__uint_as_float(pk[2 * i]), rs_hi[2 * i], __uint_as_float(pk[2 * i + 1]), rs_hi[2 * i + 1]);
+              tmem_st8(s_addr + g * 8, p8);
+            } else {
+              tmem_st16(s_addr + g * 16, pk);
+            }
           };
           group_p(r0, 0);
           group_p(r1, 1);
@@ -493,7 +524,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
         mbar_wait(smem_u32(&bars->o_final), 0, 10 + t);
         tc_fence_after();
       }
-      const float inv_l = l_run > 0.f ? 1.f / l_run : 0.f;
+      const float inv_l = (l_run > 0.f ? 1.f / l_run : 0.f) * (args.v_scale ? __ldg(&args.v_scale[bh]) : 1.f);
       long long out_row = q;
       if (row_ok && args.o_rows) out_row = __ldg(&args.o_rows[static_cast<size_t>(bh) * args.S + q]);
       uint16_t* optr = reinterpret_cast<uint16_t*>(args.o) + bh * args.o_head_stride +
@@ -533,7 +564,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
       }
       if (row_ok && args.lse) {
         // natural-log LSE of the scaled scores; -inf for rows that saw no key
-        const float lse = l_run > 0.f ? (m_used * c + log2f(l_run)) * 0.6931471805599453f : -INFINITY;
+        const float lse = l_run > 0.f ? (m_used * c - kPOff + log2f(l_run)) * 0.6931471805599453f : -INFINITY;
         args.lse[static_cast<size_t>(bh) * args.S + out_row] = lse;
       }
     }

@@ -174,6 +174,26 @@ __device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_
       : "memory");
 }
 
+// kind::f8f6f4 (e4m3 / e5m2 inputs, fp32 accumulate): same operand forms, K = 32 per instruction
+__device__ __forceinline__ void mma_ss_f8(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                          uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}\n"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mma_ts_f8(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc,
+                                          uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], [%1], %2, %3, p;\n\t}\n"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 // Shared-memory matrix descriptor (64 bit).
 //   [0,14)  start address >> 4        [16,30) leading byte offset >> 4
 //   [32,46) stride byte offset >> 4   [46,48) version = 1 on sm_100
@@ -201,6 +221,11 @@ __device__ __forceinline__ uint64_t desc_mnmajor_sw128(uint32_t saddr, uint32_t 
 // Instruction descriptor (32 bit) for kind::f16, fp32 accumulate.
 //   [4,6) c_format: 1 = f32   [7,10) a_format, [10,13) b_format: 0 = f16, 1 = bf16
 //   [15] a_major, [16] b_major: 0 = K-major, 1 = MN-major   [17,23) N >> 3   [24,29) M >> 4
+// kind::f8f6f4 with e4m3 A and B (format code 0), fp32 accumulate
+__host__ __device__ constexpr uint32_t make_idesc_e4m3(int M, int N, bool a_mn, bool b_mn) {
+  return (1u << 4) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+         (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
+}
 __host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool bf16, bool a_mn, bool b_mn) {
   return (1u << 4) | ((bf16 ? 1u : 0u) << 7) | ((bf16 ? 1u : 0u) << 10) | ((a_mn ? 1u : 0u) << 15) |
          ((b_mn ? 1u : 0u) << 16) | (static_cast<uint32_t>(N >> 3) << 17) |
@@ -234,6 +259,12 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
       "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]),
       "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]),
       "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
       : "memory");
 }
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
@@ -306,6 +337,14 @@ __device__ __forceinline__ void ex2_poly2(uint64_t x2, float& o0, float& o1) {
   unpack_f32x2(t, t0, t1);
   o0 = __int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23));
   o1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
+}
+
+// four fp32 -> four e4m3 bytes (first element in the lowest byte), round-to-nearest, saturating
+__device__ __forceinline__ uint32_t pack4_e4m3(float a, float b, float c, float d) {
+  uint16_t lo, hi;
+  asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(lo) : "f"(b), "f"(a));
+  asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(hi) : "f"(d), "f"(c));
+  return static_cast<uint32_t>(lo) | (static_cast<uint32_t>(hi) << 16);
 }
 
 // pack two fp32 -> {lo, hi} 16-bit pair (lo = first element)

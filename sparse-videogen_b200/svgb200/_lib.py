@@ -43,6 +43,8 @@ _PROTOS = {
     "svgb_attn_plan_band": [_i, _i, _i, _i, _i, _i, _vp, _sz, _pplan, _vp],
     "svgb_attn_fwd": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _ll, _ll, _ll, _ll, _f, _pplan, _vp, _vp],
     "svgb_attn_fwd_gather": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _ll, _ll, _ll, _ll, _f, _pplan, _vp, _vp],
+    "svgb_quantize_e4m3": [_vp, _i, _vp, _vp, _i, _i, _i, _vp],
+    "svgb_attn_fwd_fp8": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _ll, _ll, _ll, _ll, _f, _pplan, _vp, _vp],
     "svgb_density": [_vp, _vp, _vp, _i, _i, _i, _vp, _vp],
     "svgb_argsort_labels_bytes": [_i, _i, _i, _psz],
     "svgb_argsort_labels": [_vp, _i, _i, _i, _vp, _vp, _vp, _sz, _vp],

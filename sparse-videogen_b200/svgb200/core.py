@@ -156,6 +156,43 @@ def attn_fwd(q, k, v, plan: AttnPlan, *, layout: str = "bhsd", o_rows: Optional[
     return (o, lse) if return_lse else o
 
 
+def quantize_e4m3(x: torch.Tensor):
+    """Per-head absmax quantisation of a 16-bit [..., S, D] tensor to fp8 e4m3 bytes.
+    Returns (x8 uint8 same shape, scale fp32 [BH]) with x ~= x8.view(float8_e4m3fn) * scale[h]."""
+    _need_cuda(x)
+    S, D = x.shape[-2], x.shape[-1]
+    xc = x.contiguous()
+    BH = xc.numel() // (S * D)
+    x8 = torch.empty(xc.shape, dtype=torch.uint8, device=x.device)
+    scale = torch.empty(BH, dtype=torch.float32, device=x.device)
+    check(lib().svgb_quantize_e4m3(xc.data_ptr(), _dt(x), x8.data_ptr(), scale.data_ptr(), BH, S, D, _stream(x)),
+          "svgb_quantize_e4m3")
+    _bump(3)
+    return x8, scale
+
+
+def attn_fwd_fp8(q8, k8, v8, q_scale, k_scale, v_scale, plan: AttnPlan, *, o_rows: Optional[torch.Tensor] = None,
+                 return_lse: bool = False, sm_scale: Optional[float] = None):
+    """FP8 (e4m3) block-sparse attention: q8,k8,v8 uint8 [B,H,S,128] + per-head scales -> bf16 [B,H,S,128]."""
+    _need_cuda(q8, k8, v8, q_scale, k_scale, v_scale)
+    if not (q8.dtype == k8.dtype == v8.dtype == torch.uint8) or not (q8.shape == k8.shape == v8.shape):
+        raise SvgbError("q8, k8, v8 must be uint8 tensors of one shape")
+    B, H, S, D = q8.shape
+    BH = B * H
+    o = torch.empty(B, H, S, D, dtype=torch.bfloat16, device=q8.device)
+    lse = torch.empty(BH, S, dtype=torch.float32, device=q8.device) if return_lse else None
+    if o_rows is not None:
+        o_rows = o_rows.reshape(BH, S).to(torch.int32).contiguous()
+    scale = float(D) ** -0.5 if sm_scale is None else float(sm_scale)
+    check(lib().svgb_attn_fwd_fp8(q8.contiguous().data_ptr(), k8.contiguous().data_ptr(), v8.contiguous().data_ptr(),
+                                  q_scale.contiguous().data_ptr(), k_scale.contiguous().data_ptr(),
+                                  v_scale.contiguous().data_ptr(), o.data_ptr(), _p(lse), _p(o_rows), BH, S, D,
+                                  D, S * D, D, S * D, scale, C.byref(plan.desc), plan.ws.data_ptr(), _stream(q8)),
+          "svgb_attn_fwd_fp8")
+    _bump()
+    return (o, lse) if return_lse else o
+
+
 def density(block_map, row_sz, col_sz):
     _need_cuda(block_map, row_sz, col_sz)
     BH, QC, KC = block_map.shape

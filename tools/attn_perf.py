@@ -74,3 +74,13 @@ for QC, KC, rho, heads in [(465, 931, 0.3, 24), (400, 1000, 0.3, 24), (400, 1000
     plg = core.plan_varblock(bm.to(dev), row.to(dev), col.to(dev), S, ws=torch.empty_like(pl.ws), gather=True)
     ms = t(lambda: core.attn_fwd(qq, kk, vv, plg))
     emit(case=f"varblock_GATHER_QC{QC}_KC{KC}_rho{rho}_h{heads}", ms=ms, tflops=fl / ms / 1e9)
+
+# ---- FP8 (e4m3) path on the band mask and the dense map
+try:
+    (q8, sq), (k8, sk), (v8, sv) = (core.quantize_e4m3(x) for x in (q, k, v))
+    ms = t(lambda: core.attn_fwd_fp8(q8, k8, v8, sq, sk, sv, plan))
+    emit(case="FP8_band_hy_rho0.30", ms=ms, tflops=4.0 * D * bench.band_pairs(W) * H / ms / 1e9)
+    ms = t(lambda: core.quantize_e4m3(q))
+    emit(case="quantize_e4m3_one_tensor", ms=ms, gbs=q.numel() * 3 / ms / 1e6)
+except Exception as e:  # noqa: BLE001
+    emit(case="FP8", error=repr(e)[:300])
