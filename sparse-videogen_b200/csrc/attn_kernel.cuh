@@ -44,8 +44,10 @@ struct AttnCfg {
   static constexpr int kMaxRunsSmem = kTileBytes / 8 - 1;
   static constexpr int kQBytes = 2 * kTileBytes;
   static constexpr int kRingBytes = kStages * kTileBytes;
-  static constexpr int kBarBytes = 1024;
-  static constexpr int kSmemBytes = 1024 /*align slack*/ + kQBytes + kRingBytes + kBarBytes;
+  static constexpr int kBarBytes = 3072;
+  // no alignment slack: the dynamic window starts 1 KB into the CTA's shared memory (driver-reserved), i.e.
+  // 1024-byte aligned; the kernel traps if that ever stops being true
+  static constexpr int kSmemBytes = kQBytes + kRingBytes + kBarBytes;
   static constexpr int kThreads = 384;
   static constexpr uint32_t kTmemCols = 512;
   static constexpr int kSCol0 = 0, kSCol1 = 128, kOCol0 = 256, kOCol1 = 256 + D;
@@ -59,6 +61,8 @@ struct AttnBars {
   uint64_t kv_full[8];
   uint64_t kv_empty[8];
   uint32_t tmem_base;
+  uint32_t pad_[3];
+  float xch[2 * 2 * 128];  // row-max / row-sum exchange between the two halves of a row (double-buffered)
 };
 
 constexpr float kRescaleTau = 8.0f;  // log2 units
@@ -90,8 +94,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
   const int nchunks = gather ? (total_kv + kChunkCols - 1) / kChunkCols : item.w;
 
   extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t smem_base = smem_u32(smem_raw);
+  if (smem_base & 1023u) __trap();  // 128-byte-swizzled tiles need a 1024-byte aligned base
+  uint8_t* smem_al = smem_raw;
   const uint32_t sQ = smem_base;
   const uint32_t sRing = smem_base + Cfg::kQBytes;
   AttnBars* bars = reinterpret_cast<AttnBars*>(smem_al + Cfg::kQBytes + Cfg::kRingBytes);
@@ -114,7 +119,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
     mbar_init(smem_u32(&bars->o_final), 1);
     for (int t = 0; t < 2; ++t) {
       mbar_init(smem_u32(&bars->s_full[t]), 1);
-      mbar_init(smem_u32(&bars->p_full[t]), 128);
+      mbar_init(smem_u32(&bars->p_full[t]), 256);
     }
     for (int s = 0; s < kStages; ++s) {
       mbar_init(smem_u32(&bars->kv_full[s]), n_prod);
@@ -367,205 +372,226 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
     setmaxnreg_dec<kRegsLight>();
   } else {
     // ------------------------------------------------------------------ softmax / correction / epilogue
+    // Both softmax warpgroups work on the SAME tile at a time, alternating T0, T1, T0, ...: thread (half, row)
+    // owns 64 of the 128 key columns of one query row (half 0 = warps 4-7, half 1 = warps 8-11; both map to
+    // the same TMEM lanes).  While they process T0's chunk the tensor core runs T1's PV / QK, so the softmax
+    // units stay busy and the per-tile latency on the MMA critical chain is halved.  The two halves of a row
+    // agree on the row maximum through shared memory (one named barrier per tile-chunk); row sums are only
+    // combined in the epilogue.
     setmaxnreg_inc<kRegsSoftmax>();
-    const int t = (warp - 4) >> 2;
-    if (t < ntiles) {
+    {
+      const int half = (warp - 4) >> 2;
       const int wq = warp & 3;
       const int row = wq * 32 + lane;  // row inside the 128-row tile == TMEM lane
-      const int q = q_row0 + t * kTileRows + row;
-      const int qm = (args.q_index && q < args.S) ? __ldg(&args.q_index[q]) : q;  // position seen by the mask
       const uint32_t lane_addr = tmem + (static_cast<uint32_t>(wq * 32) << 16);
-      const uint32_t s_addr = lane_addr + (t == 0 ? Cfg::kSCol0 : Cfg::kSCol1);
-      const uint32_t o_addr = lane_addr + (t == 0 ? Cfg::kOCol0 : Cfg::kOCol1);
       // fp8: logits carry s_q * s_k; P = 2^(x - m + 4) with the lazy-rescale slack at 4 keeps P in (0, 2^8]
       // (e4m3 max 448) while the fresh-max case still has 13 binades below it
       const float c = args.scale_log2 * (args.q_scale ? __ldg(&args.q_scale[bh]) * __ldg(&args.k_scale[bh]) : 1.f);
       constexpr float kTau = FP8 ? 4.f : kRescaleTau;
       constexpr float kPOff = FP8 ? 4.f : 0.f;
       const int mode = args.mask_mode, m0 = args.m0, m1 = args.m1, m2 = args.m2;
-      const uint32_t sbar = smem_u32(&bars->s_full[t]);
-      const uint32_t pbar = smem_u32(&bars->p_full[t]);
+      float* xch = bars->xch;  // [2 parity][2 half][128 rows]
+      int xstep = 0;
+      // exchange one float with the thread that owns the other half of this row
+      auto exchange = [&](float v) -> float {
+        float* buf = xch + (xstep & 1) * 256;
+        buf[half * 128 + row] = v;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const float other = buf[(half ^ 1) * 128 + row];
+        ++xstep;
+        return other;
+      };
 
-      float m_used = -INFINITY;  // reference max the stored P / O are scaled against
-      float l_run = 0.f;
+      float m_used[2] = {-INFINITY, -INFINITY};  // per tile: reference max the stored P / O are scaled against
+      float l_run[2] = {0.f, 0.f};               // per tile: this thread's half of the row sum
       int2 ch = (nchunks > 0 && !gather) ? __ldg(&chunks[0]) : make_int2(0, 0);
-      MaskRow mrow;
-      mrow.init(mode, qm, m0, m1, m2);
 
       for (int j = 0; j < nchunks; ++j) {
         const int kv0 = ch.x;
         const int valid = gather ? min(kChunkCols, total_kv - j * kChunkCols) : chunk_valid(ch.y);
         const bool elem = !gather && (ch.y & kChunkElem) != 0;
         const int ncols = (valid + Cfg::kMmaK - 1) & ~(Cfg::kMmaK - 1);
-        const int ngroups = (ncols + 31) >> 5;
         if (!gather && j + 1 < nchunks) ch = __ldg(&chunks[j + 1]);
+        const int c0 = half * 64;            // first key column of this thread's half
+        const int mycols = ncols - c0;       // <= 0: nothing in this half (narrow chunk)
 
-        mbar_wait(sbar, j & 1, 8 + t);
-        tc_fence_after();
+#pragma unroll 1
+        for (int t = 0; t < ntiles; ++t) {
+          const uint32_t s_addr = lane_addr + (t == 0 ? Cfg::kSCol0 : Cfg::kSCol1);
+          const uint32_t o_addr = lane_addr + (t == 0 ? Cfg::kOCol0 : Cfg::kOCol1);
+          const int q = q_row0 + t * kTileRows + row;
+          mbar_wait(smem_u32(&bars->s_full[t]), j & 1, 8 + t);
+          tc_fence_after();
 
-        // ---------------- single pass: the whole score row (<=128 columns) lives in registers.
-        // Compiled twice: kPlain = full unmasked 128-column chunk (the common case, no guards at all) and
-        // the general form, which first overwrites disallowed scores with -inf in place (run tails,
-        // band edges, profiling masks) -- exp2(-inf) = 0 then makes the rest identical to the plain path.
-        float rs;
-        auto chunk_body = [&](auto plain_tag) {
-          constexpr bool kPlain = decltype(plain_tag)::value;
-          uint32_t r0[32], r1[32], r2[32], r3[32];
-          tmem_ld32(s_addr, r0);
-          if (kPlain || ngroups > 1) tmem_ld32(s_addr + 32, r1);
-          if (kPlain || ngroups > 2) tmem_ld32(s_addr + 64, r2);
-          if (kPlain || ngroups > 3) tmem_ld32(s_addr + 96, r3);
-          tc_wait_ld();
-          if constexpr (!kPlain) {
-            auto sanitize = [&](uint32_t(&rr)[32], int g) {
-              const int left = valid - g * 32;
-              if (g >= ngroups || !(elem || left < 32)) return;  // warp-uniform
-              uint32_t bits = left >= 32 ? 0xffffffffu : (1u << left) - 1u;
-              if (elem) bits &= mrow.bits32(kv0 + g * 32);
+          float rs;
+          auto chunk_body = [&](auto plain_tag) {
+            constexpr bool kPlain = decltype(plain_tag)::value;
+            uint32_t ra[32], rb[32];  // columns [c0, c0+32) and [c0+32, c0+64)
+            if (kPlain || mycols > 0) tmem_ld32(s_addr + c0, ra);
+            if (kPlain || mycols > 32) tmem_ld32(s_addr + c0 + 32, rb);
+            tc_wait_ld();
+            if constexpr (!kPlain) {
+              auto sanitize = [&](uint32_t(&rr)[32], int g) {  // g: global 32-column group index (0..3)
+                const int left = valid - g * 32;
+                if (g * 32 >= ncols || !(elem || left < 32)) return;  // warp-uniform
+                uint32_t bits = left >= 32 ? 0xffffffffu : (left > 0 ? (1u << left) - 1u : 0u);
+                if (elem && left > 0) {
+                  const int qm = (args.q_index && q < args.S) ? __ldg(&args.q_index[q]) : q;
+                  MaskRow mrow;
+                  mrow.init(mode, qm, m0, m1, m2);
+                  bits &= mrow.bits32(kv0 + g * 32);
+                }
 #pragma unroll
-              for (int i = 0; i < 32; ++i) rr[i] = (bits >> i) & 1u ? rr[i] : 0xff800000u;  // -inf
+                for (int i = 0; i < 32; ++i) rr[i] = (bits >> i) & 1u ? rr[i] : 0xff800000u;  // -inf
+              };
+              sanitize(ra, 2 * half);
+              sanitize(rb, 2 * half + 1);
+            }
+            float mx = -INFINITY;
+            if (kPlain || mycols > 0) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(ra[i]));
+            }
+            if (kPlain || mycols > 32) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(rb[i]));
+            }
+            const float m_new = fmaxf(m_used[t], fmaxf(mx, exchange(mx)));
+            // lazy rescale: keep the stale reference max unless it grew by more than tau (log2 units)
+            float alpha = 1.f;
+            if ((m_new - m_used[t]) * c > kTau) {  // false when both are -inf (NaN compare)
+              alpha = ex2_approx((m_used[t] - m_new) * c);  // 0 when m_used == -inf
+              m_used[t] = m_new;
+            }
+            if (j > 0 && __any_sync(0xffffffffu, alpha != 1.f)) {
+              // correction of this thread's half of the O row (PV_t(j-1) is complete: S_t(j) commit covered it)
+#pragma unroll 1
+              for (int g = 0; g < D / 64; ++g) {
+                uint32_t o[32];
+                tmem_ld32(o_addr + half * (D / 2) + g * 32, o);
+                tc_wait_ld();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                tmem_st32(o_addr + half * (D / 2) + g * 32, o);
+              }
+            }
+            l_run[t] *= alpha;
+            const float mc = (m_used[t] == -INFINITY) ? 0.f : m_used[t] * c - kPOff;
+            const uint64_t c2 = pack_f32x2(c, c), nmc2 = pack_f32x2(-mc, -mc);
+            uint64_t sum2 = pack_f32x2(0.f, 0.f);
+            // P = exp2(S*c - m*c) -> 16-bit (or e4m3), packed over the first half of the S tile.  Every 4th
+            // pair is evaluated on the FMA pipe (polynomial) to unload the MUFU.
+            auto group_p = [&](const uint32_t(&rr)[32], int g) {  // g: global group index
+              if constexpr (!kPlain) {
+                if (g * 32 >= ncols) return;
+              }
+              uint32_t pk[16];
+              float rs_hi[FP8 ? 16 : 1];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const uint64_t x2 =
+                    ffma2(pack_f32x2(__uint_as_float(rr[2 * i]), __uint_as_float(rr[2 * i + 1])), c2, nmc2);
+                float p0, p1;
+                if ((i & 3) == 3) {
+                  ex2_poly2(x2, p0, p1);
+                } else {
+                  float x0, x1;
+                  unpack_f32x2(x2, x0, x1);
+                  p0 = ex2_approx(x0);
+                  p1 = ex2_approx(x1);
+                }
+                sum2 = fadd2(sum2, pack_f32x2(p0, p1));
+                if constexpr (FP8) {  // keep the fp32 pair; four of them make one e4m3x4 word below
+                  pk[i] = __float_as_uint(p0);
+                  rs_hi[i] = p1;
+                } else {
+                  pk[i] = pack2<BF16>(p0, p1);
+                }
+              }
+              if constexpr (FP8) {
+                uint32_t p8[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                  p8[i] = pack4_e4m3(__uint_as_float(pk[2 * i]), rs_hi[2 * i], __uint_as_float(pk[2 * i + 1]),
+                                     rs_hi[2 * i + 1]);
+                tmem_st8(s_addr + g * 8, p8);
+              } else {
+                tmem_st16(s_addr + g * 16, pk);
+              }
             };
-            sanitize(r0, 0);
-            sanitize(r1, 1);
-            sanitize(r2, 2);
-            sanitize(r3, 3);
-          }
-          auto group_max = [&](const uint32_t(&rr)[32], int g) -> float {
-            float m = -INFINITY;
-            if constexpr (!kPlain) {
-              if (g >= ngroups) return m;
-            }
-#pragma unroll
-            for (int i = 0; i < 32; ++i) m = fmaxf(m, __uint_as_float(rr[i]));
-            return m;
+            group_p(ra, 2 * half);
+            group_p(rb, 2 * half + 1);
+            float s0, s1;
+            unpack_f32x2(sum2, s0, s1);
+            rs = s0 + s1;
           };
-          const float mx = fmaxf(fmaxf(group_max(r0, 0), group_max(r1, 1)), fmaxf(group_max(r2, 2), group_max(r3, 3)));
-          const float m_new = fmaxf(m_used, mx);
-          // lazy rescale: keep the stale reference max unless it grew by more than tau (log2 units)
-          float alpha = 1.f;
-          if ((m_new - m_used) * c > kTau) {  // false when both are -inf (NaN compare)
-            alpha = ex2_approx((m_used - m_new) * c);  // 0 when m_used == -inf
-            m_used = m_new;
-          }
-          if (j > 0 && __any_sync(0xffffffffu, alpha != 1.f)) {
-            // correction: O_row *= alpha (PV_t(j-1) is complete: the S_t(j) commit covered it)
-#pragma unroll 1
-            for (int g = 0; g < D / 32; ++g) {
-              uint32_t o[32];
-              tmem_ld32(o_addr + g * 32, o);
-              tc_wait_ld();
-#pragma unroll
-              for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-              tmem_st32(o_addr + g * 32, o);
-            }
-          }
-          l_run *= alpha;
-          const float mc = (m_used == -INFINITY) ? 0.f : m_used * c - kPOff;
-          const uint64_t c2 = pack_f32x2(c, c), nmc2 = pack_f32x2(-mc, -mc);
-          uint64_t sum2 = pack_f32x2(0.f, 0.f);
-          // P = exp2(S*c - m*c) -> 16-bit, packed two per TMEM column over the first half of the S tile.
-          // Every 4th pair is evaluated on the FMA pipe (polynomial) to unload the MUFU.
-          auto group_p = [&](const uint32_t(&rr)[32], int g) {
-            if constexpr (!kPlain) {
-              if (g >= ngroups) return;
-            }
-            uint32_t pk[16];
-            float rs_hi[FP8 ? 16 : 1];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const uint64_t x2 =
-                  ffma2(pack_f32x2(__uint_as_float(rr[2 * i]), __uint_as_float(rr[2 * i + 1])), c2, nmc2);
-              float p0, p1;
-              if ((i & 3) == 3) {
-                ex2_poly2(x2, p0, p1);
-              } else {
-                float x0, x1;
-                unpack_f32x2(x2, x0, x1);
-                p0 = ex2_approx(x0);
-                p1 = ex2_approx(x1);
-              }
-              sum2 = fadd2(sum2, pack_f32x2(p0, p1));
-              if constexpr (FP8) {  // keep the fp32 pair; four of them make one e4m3x4 word below
-                pk[i] = __float_as_uint(p0);
-                rs_hi[i] = p1;
-              } else {
-                pk[i] = pack2<BF16>(p0, p1);
-              }
-            }
-            if constexpr (FP8) {
-              uint32_t p8[8];
-#pragma unroll
-              for (int i = 0; i < 8; ++i)
-                p8[i] = pack4_e4m3(__uint_as_float(pk[2 * i]), rs_hi[2 * i], __uint_as_float(pk[2 * i + 1]), rs_hi[2 * i + 1]);
-              tmem_st8(s_addr + g * 8, p8);
-            } else {
-              tmem_st16(s_addr + g * 16, pk);
-            }
-          };
-          group_p(r0, 0);
-          group_p(r1, 1);
-          group_p(r2, 2);
-          group_p(r3, 3);
-          float s0, s1;
-          unpack_f32x2(sum2, s0, s1);
-          rs = s0 + s1;
-        };
-        if (!elem && valid == kChunkCols) chunk_body(std::true_type{});
-        else chunk_body(std::false_type{});
-        l_run += rs;
-        tc_wait_st();
-        tc_fence_before();
-        mbar_arrive(pbar);
+          if (!elem && valid == kChunkCols) chunk_body(std::true_type{});
+          else chunk_body(std::false_type{});
+
+          l_run[t] += rs;
+          tc_wait_st();
+          tc_fence_before();
+          mbar_arrive(smem_u32(&bars->p_full[t]));
+        }
       }
 
-      // ---------------- epilogue: O / l -> 16-bit -> global (optionally scattered rows)
-      const bool row_ok = (t * kTileRows + row) < nrows;
+      // ---------------- epilogue: O / l -> 16-bit -> global (optionally scattered rows); each thread stores its
+      // half of the D output columns of both tiles' rows
       if (nchunks > 0) {
-        mbar_wait(smem_u32(&bars->o_final), 0, 10 + t);
+        mbar_wait(smem_u32(&bars->o_final), 0, 10);
         tc_fence_after();
       }
-      const float inv_l = (l_run > 0.f ? 1.f / l_run : 0.f) * (args.v_scale ? __ldg(&args.v_scale[bh]) : 1.f);
-      long long out_row = q;
-      if (row_ok && args.o_rows) out_row = __ldg(&args.o_rows[static_cast<size_t>(bh) * args.S + q]);
-      uint16_t* optr = reinterpret_cast<uint16_t*>(args.o) + bh * args.o_head_stride +
-                       out_row * args.o_row_stride;
-      float* optr32 = reinterpret_cast<float*>(args.o) + bh * args.o_head_stride + out_row * args.o_row_stride;
 #pragma unroll 1
-      for (int g = 0; g < D / 32; ++g) {
-        uint32_t o[32];
-        if (nchunks > 0) {
-          tmem_ld32(o_addr + g * 32, o);
-          tc_wait_ld();
-        } else {
+      for (int t = 0; t < ntiles; ++t) {
+        const uint32_t o_addr = lane_addr + (t == 0 ? Cfg::kOCol0 : Cfg::kOCol1);
+        const int q = q_row0 + t * kTileRows + row;
+        const bool row_ok = (t * kTileRows + row) < nrows;
+        const float l_tot = l_run[t] + exchange(l_run[t]);
+        const float inv_l = (l_tot > 0.f ? 1.f / l_tot : 0.f) * (args.v_scale ? __ldg(&args.v_scale[bh]) : 1.f);
+        long long out_row = q;
+        if (row_ok && args.o_rows) out_row = __ldg(&args.o_rows[static_cast<size_t>(bh) * args.S + q]);
+        const int col0 = half * (D / 2);
+        uint16_t* optr = reinterpret_cast<uint16_t*>(args.o) + bh * args.o_head_stride +
+                         out_row * args.o_row_stride + col0;
+        float* optr32 = reinterpret_cast<float*>(args.o) + bh * args.o_head_stride + out_row * args.o_row_stride + col0;
+#pragma unroll 1
+        for (int g = 0; g < D / 64; ++g) {
+          uint32_t o[32];
+          if (nchunks > 0) {
+            tmem_ld32(o_addr + col0 + g * 32, o);
+            tc_wait_ld();
+          } else {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) o[i] = 0u;
-        }
-        if (row_ok && args.out_f32) {
-#pragma unroll
-          for (int v = 0; v < 8; ++v) {
-            float4 w;
-            w.x = __uint_as_float(o[4 * v + 0]) * inv_l;
-            w.y = __uint_as_float(o[4 * v + 1]) * inv_l;
-            w.z = __uint_as_float(o[4 * v + 2]) * inv_l;
-            w.w = __uint_as_float(o[4 * v + 3]) * inv_l;
-            *reinterpret_cast<float4*>(optr32 + g * 32 + v * 4) = w;
+            for (int i = 0; i < 32; ++i) o[i] = 0u;
           }
-        } else if (row_ok) {
+          if (row_ok && args.out_f32) {
 #pragma unroll
-          for (int v = 0; v < 4; ++v) {
-            uint4 w;
-            w.x = pack2<BF16>(__uint_as_float(o[8 * v + 0]) * inv_l, __uint_as_float(o[8 * v + 1]) * inv_l);
-            w.y = pack2<BF16>(__uint_as_float(o[8 * v + 2]) * inv_l, __uint_as_float(o[8 * v + 3]) * inv_l);
-            w.z = pack2<BF16>(__uint_as_float(o[8 * v + 4]) * inv_l, __uint_as_float(o[8 * v + 5]) * inv_l);
-            w.w = pack2<BF16>(__uint_as_float(o[8 * v + 6]) * inv_l, __uint_as_float(o[8 * v + 7]) * inv_l);
-            *reinterpret_cast<uint4*>(optr + g * 32 + v * 8) = w;
+            for (int v = 0; v < 8; ++v) {
+              float4 w;
+              w.x = __uint_as_float(o[4 * v + 0]) * inv_l;
+              w.y = __uint_as_float(o[4 * v + 1]) * inv_l;
+              w.z = __uint_as_float(o[4 * v + 2]) * inv_l;
+              w.w = __uint_as_float(o[4 * v + 3]) * inv_l;
+              *reinterpret_cast<float4*>(optr32 + g * 32 + v * 4) = w;
+            }
+          } else if (row_ok) {
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+              uint4 w;
+              w.x = pack2<BF16>(__uint_as_float(o[8 * v + 0]) * inv_l, __uint_as_float(o[8 * v + 1]) * inv_l);
+              w.y = pack2<BF16>(__uint_as_float(o[8 * v + 2]) * inv_l, __uint_as_float(o[8 * v + 3]) * inv_l);
+              w.z = pack2<BF16>(__uint_as_float(o[8 * v + 4]) * inv_l, __uint_as_float(o[8 * v + 5]) * inv_l);
+              w.w = pack2<BF16>(__uint_as_float(o[8 * v + 6]) * inv_l, __uint_as_float(o[8 * v + 7]) * inv_l);
+              *reinterpret_cast<uint4*>(optr + g * 32 + v * 8) = w;
+            }
           }
         }
-      }
-      if (row_ok && args.lse) {
-        // natural-log LSE of the scaled scores; -inf for rows that saw no key
-        const float lse = l_run > 0.f ? (m_used * c - kPOff + log2f(l_run)) * 0.6931471805599453f : -INFINITY;
-        args.lse[static_cast<size_t>(bh) * args.S + out_row] = lse;
+        if (row_ok && args.lse && half == 0) {
+          // natural-log LSE of the scaled scores; -inf for rows that saw no key
+          const float lse =
+              l_tot > 0.f ? (m_used[t] * c - kPOff + log2f(l_tot)) * 0.6931471805599453f : -INFINITY;
+          args.lse[static_cast<size_t>(bh) * args.S + out_row] = lse;
+        }
       }
     }
   }
