@@ -406,7 +406,8 @@ static int plan_varblock_impl(const uint8_t* map, const int32_t* row_sz, const i
   plan->counts_stride = 1;
   plan->mask_mode = MASK_NONE;
   plan->m0 = gather ? (KC + 1) / 2 + 1 : 0;  // gather: upper bound of runs per q-block (kernel smem table)
-  plan->m1 = plan->m2 = 0;
+  plan->m1 = S / KC;                          // average key-cluster size (selects the softmax thread mapping)
+  plan->m2 = 0;
   plan->counts_off = 0;
   plan->items_off = align_up(sizeof(int) * BH, 256);
   plan->chunks_off = plan->items_off + align_up(sizeof(int4) * BH * max_items, 256);
@@ -514,6 +515,8 @@ static int attn_fwd_entry(const void* q, const void* k, const void* v, const flo
   a.m2 = plan->m2;
   a.q_index = nullptr;
   a.out_f32 = 0;
+  // variable-block plans over small key clusters are made of narrow chunks: latency-bound steps
+  a.softmax_shared = (plan->kind == 1 && plan->m1 > 0 && plan->m1 < 256) ? 1 : 0;
   a.q_scale = q_scale;
   a.k_scale = k_scale;
   a.v_scale = v_scale;

@@ -86,6 +86,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
   const int4 item = args.items[static_cast<size_t>(bh) * args.items_stride + blockIdx.x];
   const int q_row0 = item.x, nrows = item.y, chunk0 = item.z;
   const int ntiles = nrows > kTileRows ? 2 : 1;
+  const bool per_tile_map = ntiles == 2 && !args.softmax_shared;  // softmax thread mapping (see below)
   const int2* __restrict__ chunks = args.chunks + chunk0;
   constexpr bool gather = kGather;
   // gather mode: item.w = number of runs, chunks are implicit (128 selected keys each, last one partial)
@@ -119,7 +120,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
     mbar_init(smem_u32(&bars->o_final), 1);
     for (int t = 0; t < 2; ++t) {
       mbar_init(smem_u32(&bars->s_full[t]), 1);
-      mbar_init(smem_u32(&bars->p_full[t]), 256);
+      mbar_init(smem_u32(&bars->p_full[t]), per_tile_map ? 128 : 256);
     }
     for (int s = 0; s < kStages; ++s) {
       mbar_init(smem_u32(&bars->kv_full[s]), n_prod);
@@ -379,6 +380,214 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
     // agree on the row maximum through shared memory (one named barrier per tile-chunk); row sums are only
     // combined in the epilogue.
     setmaxnreg_inc<kRegsSoftmax>();
+    if (per_tile_map) {
+    // ---- two-tile items: one warpgroup per tile, one thread per query row (the two tiles' softmaxes run
+    // concurrently on different warps, so their latency bubbles overlap)
+    const int t = (warp - 4) >> 2;
+    if (t < ntiles) {
+      const int wq = warp & 3;
+      const int row = wq * 32 + lane;  // row inside the 128-row tile == TMEM lane
+      const int q = q_row0 + t * kTileRows + row;
+      const int qm = (args.q_index && q < args.S) ? __ldg(&args.q_index[q]) : q;  // position seen by the mask
+      const uint32_t lane_addr = tmem + (static_cast<uint32_t>(wq * 32) << 16);
+      const uint32_t s_addr = lane_addr + (t == 0 ? Cfg::kSCol0 : Cfg::kSCol1);
+      const uint32_t o_addr = lane_addr + (t == 0 ? Cfg::kOCol0 : Cfg::kOCol1);
+      // fp8: logits carry s_q * s_k; P = 2^(x - m + 4) with the lazy-rescale slack at 4 keeps P in (0, 2^8]
+      // (e4m3 max 448) while the fresh-max case still has 13 binades below it
+      const float c = args.scale_log2 * (args.q_scale ? __ldg(&args.q_scale[bh]) * __ldg(&args.k_scale[bh]) : 1.f);
+      constexpr float kTau = FP8 ? 4.f : kRescaleTau;
+      constexpr float kPOff = FP8 ? 4.f : 0.f;
+      const int mode = args.mask_mode, m0 = args.m0, m1 = args.m1, m2 = args.m2;
+      const uint32_t sbar = smem_u32(&bars->s_full[t]);
+      const uint32_t pbar = smem_u32(&bars->p_full[t]);
+
+      float m_used = -INFINITY;  // reference max the stored P / O are scaled against
+      float l_run = 0.f;
+      int2 ch = (nchunks > 0 && !gather) ? __ldg(&chunks[0]) : make_int2(0, 0);
+      MaskRow mrow;
+      mrow.init(mode, qm, m0, m1, m2);
+
+      for (int j = 0; j < nchunks; ++j) {
+        const int kv0 = ch.x;
+        const int valid = gather ? min(kChunkCols, total_kv - j * kChunkCols) : chunk_valid(ch.y);
+        const bool elem = !gather && (ch.y & kChunkElem) != 0;
+        const int ncols = (valid + Cfg::kMmaK - 1) & ~(Cfg::kMmaK - 1);
+        const int ngroups = (ncols + 31) >> 5;
+        if (!gather && j + 1 < nchunks) ch = __ldg(&chunks[j + 1]);
+
+        mbar_wait(sbar, j & 1, 8 + t);
+        tc_fence_after();
+
+        // ---------------- single pass: the whole score row (<=128 columns) lives in registers.
+        // Compiled twice: kPlain = full unmasked 128-column chunk (the common case, no guards at all) and
+        // the general form, which first overwrites disallowed scores with -inf in place (run tails,
+        // band edges, profiling masks) -- exp2(-inf) = 0 then makes the rest identical to the plain path.
+        float rs;
+        auto chunk_body = [&](auto plain_tag) {
+          constexpr bool kPlain = decltype(plain_tag)::value;
+          uint32_t r0[32], r1[32], r2[32], r3[32];
+          tmem_ld32(s_addr, r0);
+          if (kPlain || ngroups > 1) tmem_ld32(s_addr + 32, r1);
+          if (kPlain || ngroups > 2) tmem_ld32(s_addr + 64, r2);
+          if (kPlain || ngroups > 3) tmem_ld32(s_addr + 96, r3);
+          tc_wait_ld();
+          if constexpr (!kPlain) {
+            auto sanitize = [&](uint32_t(&rr)[32], int g) {
+              const int left = valid - g * 32;
+              if (g >= ngroups || !(elem || left < 32)) return;  // warp-uniform
+              uint32_t bits = left >= 32 ? 0xffffffffu : (1u << left) - 1u;
+              if (elem) bits &= mrow.bits32(kv0 + g * 32);
+#pragma unroll
+              for (int i = 0; i < 32; ++i) rr[i] = (bits >> i) & 1u ? rr[i] : 0xff800000u;  // -inf
+            };
+            sanitize(r0, 0);
+            sanitize(r1, 1);
+            sanitize(r2, 2);
+            sanitize(r3, 3);
+          }
+          auto group_max = [&](const uint32_t(&rr)[32], int g) -> float {
+            float m = -INFINITY;
+            if constexpr (!kPlain) {
+              if (g >= ngroups) return m;
+            }
+#pragma unroll
+            for (int i = 0; i < 32; ++i) m = fmaxf(m, __uint_as_float(rr[i]));
+            return m;
+          };
+          const float mx = fmaxf(fmaxf(group_max(r0, 0), group_max(r1, 1)), fmaxf(group_max(r2, 2), group_max(r3, 3)));
+          const float m_new = fmaxf(m_used, mx);
+          // lazy rescale: keep the stale reference max unless it grew by more than tau (log2 units)
+          float alpha = 1.f;
+          if ((m_new - m_used) * c > kTau) {  // false when both are -inf (NaN compare)
+            alpha = ex2_approx((m_used - m_new) * c);  // 0 when m_used == -inf
+            m_used = m_new;
+          }
+          if (j > 0 && __any_sync(0xffffffffu, alpha != 1.f)) {
+            // correction: O_row *= alpha (PV_t(j-1) is complete: the S_t(j) commit covered it)
+#pragma unroll 1
+            for (int g = 0; g < D / 32; ++g) {
+              uint32_t o[32];
+              tmem_ld32(o_addr + g * 32, o);
+              tc_wait_ld();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+              tmem_st32(o_addr + g * 32, o);
+            }
+          }
+          l_run *= alpha;
+          const float mc = (m_used == -INFINITY) ? 0.f : m_used * c - kPOff;
+          const uint64_t c2 = pack_f32x2(c, c), nmc2 = pack_f32x2(-mc, -mc);
+          uint64_t sum2 = pack_f32x2(0.f, 0.f);
+          // P = exp2(S*c - m*c) -> 16-bit, packed two per TMEM column over the first half of the S tile.
+          // Every 4th pair is evaluated on the FMA pipe (polynomial) to unload the MUFU.
+          auto group_p = [&](const uint32_t(&rr)[32], int g) {
+            if constexpr (!kPlain) {
+              if (g >= ngroups) return;
+            }
+            uint32_t pk[16];
+            float rs_hi[FP8 ? 16 : 1];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const uint64_t x2 =
+                  ffma2(pack_f32x2(__uint_as_float(rr[2 * i]), __uint_as_float(rr[2 * i + 1])), c2, nmc2);
+              float p0, p1;
+              if ((i & 3) == 3) {
+                ex2_poly2(x2, p0, p1);
+              } else {
+                float x0, x1;
+                unpack_f32x2(x2, x0, x1);
+                p0 = ex2_approx(x0);
+                p1 = ex2_approx(x1);
+              }
+              sum2 = fadd2(sum2, pack_f32x2(p0, p1));
+              if constexpr (FP8) {  // keep the fp32 pair; four of them make one e4m3x4 word below
+                pk[i] = __float_as_uint(p0);
+                rs_hi[i] = p1;
+              } else {
+                pk[i] = pack2<BF16>(p0, p1);
+              }
+            }
+            if constexpr (FP8) {
+              uint32_t p8[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                p8[i] = pack4_e4m3(__uint_as_float(pk[2 * i]), rs_hi[2 * i], __uint_as_float(pk[2 * i + 1]), rs_hi[2 * i + 1]);
+              tmem_st8(s_addr + g * 8, p8);
+            } else {
+              tmem_st16(s_addr + g * 16, pk);
+            }
+          };
+          group_p(r0, 0);
+          group_p(r1, 1);
+          group_p(r2, 2);
+          group_p(r3, 3);
+          float s0, s1;
+          unpack_f32x2(sum2, s0, s1);
+          rs = s0 + s1;
+        };
+        if (!elem && valid == kChunkCols) chunk_body(std::true_type{});
+        else chunk_body(std::false_type{});
+        l_run += rs;
+        tc_wait_st();
+        tc_fence_before();
+        mbar_arrive(pbar);
+      }
+
+      // ---------------- epilogue: O / l -> 16-bit -> global (optionally scattered rows)
+      const bool row_ok = (t * kTileRows + row) < nrows;
+      if (nchunks > 0) {
+        mbar_wait(smem_u32(&bars->o_final), 0, 10 + t);
+        tc_fence_after();
+      }
+      const float inv_l = (l_run > 0.f ? 1.f / l_run : 0.f) * (args.v_scale ? __ldg(&args.v_scale[bh]) : 1.f);
+      long long out_row = q;
+      if (row_ok && args.o_rows) out_row = __ldg(&args.o_rows[static_cast<size_t>(bh) * args.S + q]);
+      uint16_t* optr = reinterpret_cast<uint16_t*>(args.o) + bh * args.o_head_stride +
+                       out_row * args.o_row_stride;
+      float* optr32 = reinterpret_cast<float*>(args.o) + bh * args.o_head_stride + out_row * args.o_row_stride;
+#pragma unroll 1
+      for (int g = 0; g < D / 32; ++g) {
+        uint32_t o[32];
+        if (nchunks > 0) {
+          tmem_ld32(o_addr + g * 32, o);
+          tc_wait_ld();
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[i] = 0u;
+        }
+        if (row_ok && args.out_f32) {
+#pragma unroll
+          for (int v = 0; v < 8; ++v) {
+            float4 w;
+            w.x = __uint_as_float(o[4 * v + 0]) * inv_l;
+            w.y = __uint_as_float(o[4 * v + 1]) * inv_l;
+            w.z = __uint_as_float(o[4 * v + 2]) * inv_l;
+            w.w = __uint_as_float(o[4 * v + 3]) * inv_l;
+            *reinterpret_cast<float4*>(optr32 + g * 32 + v * 4) = w;
+          }
+        } else if (row_ok) {
+#pragma unroll
+          for (int v = 0; v < 4; ++v) {
+            uint4 w;
+            w.x = pack2<BF16>(__uint_as_float(o[8 * v + 0]) * inv_l, __uint_as_float(o[8 * v + 1]) * inv_l);
+            w.y = pack2<BF16>(__uint_as_float(o[8 * v + 2]) * inv_l, __uint_as_float(o[8 * v + 3]) * inv_l);
+            w.z = pack2<BF16>(__uint_as_float(o[8 * v + 4]) * inv_l, __uint_as_float(o[8 * v + 5]) * inv_l);
+            w.w = pack2<BF16>(__uint_as_float(o[8 * v + 6]) * inv_l, __uint_as_float(o[8 * v + 7]) * inv_l);
+            *reinterpret_cast<uint4*>(optr + g * 32 + v * 8) = w;
+          }
+        }
+      }
+      if (row_ok && args.lse) {
+        // natural-log LSE of the scaled scores; -inf for rows that saw no key
+        const float lse = l_run > 0.f ? (m_used * c - kPOff + log2f(l_run)) * 0.6931471805599453f : -INFINITY;
+        args.lse[static_cast<size_t>(bh) * args.S + out_row] = lse;
+      }
+    }
+    } else
+    // ---- shared mapping: both warpgroups work on the same tile (each thread owns half of a row), alternating
+    // T0, T1.  Used for single-tile items (cluster tails, split-KV profiling passes: halves the lone tile's
+    // softmax latency) and for plans made of narrow chunks (small k-means clusters), where the step is
+    // latency- rather than throughput-bound and interleaving the two tiles on the same threads hides it.
     {
       const int half = (warp - 4) >> 2;
       const int wq = warp & 3;
