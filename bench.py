@@ -343,6 +343,31 @@ def run_ours(args):
                 "ms_per_call": ms, "tflops": fl / ms / 1e9, "density": fl / (4.0 * D * Hl * S * S),
                 "dense_equiv_tflops": 4.0 * D * Hl * S * S / ms / 1e9}
 
+    # ---- FP8 (e4m3) variant of the same band-mask attention (BASELINE config 5 flavour), reported beside it
+    fp8 = None
+    if rank == 0:
+        try:
+            (q8, sq), (k8, sk), (v8, sv) = (core.quantize_e4m3(x) for x in (q, k, v))
+            for _ in range(2):
+                core.attn_fwd_fp8(q8, k8, v8, sq, sk, sv, proc.block_mask.plan)
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(3):
+                core.attn_fwd_fp8(q8, k8, v8, sq, sk, sv, proc.block_mask.plan)
+            b.record()
+            torch.cuda.synchronize()
+            ms8 = a.elapsed_time(b) / 3
+            a.record()
+            core.quantize_e4m3(q)
+            b.record()
+            torch.cuda.synchronize()
+            fp8 = {"workload": f"same band mask, e4m3 Q/K/V (per-head scales), bf16 out, {Hl} heads", "ms_per_call": ms8,
+                   "tflops": flops_local / ms8 / 1e9, "quantize_ms_per_tensor": a.elapsed_time(b)}
+            del q8, k8, v8
+        except Exception as e:  # noqa: BLE001
+            fp8 = {"error": repr(e)[:200]}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -379,7 +404,7 @@ def run_ours(args):
                          "seconds": dt_cpu},
         "e2e": {"value": flops_total / e2e_ms / 1e9, "unit": "TFLOP/s", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": bytes_in, "d2h_bytes_per_step": bytes_out},
-        "clocks": clocks, "gpu_launches": launches, "svg2": svg2,
+        "clocks": clocks, "gpu_launches": launches, "svg2": svg2, "fp8": fp8,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -46,19 +46,24 @@ __global__ void smse_plan_kernel(int S, int nsplit, int n_chunks, int* counts, i
   if (threadIdx.x == 0) counts[0] = nsplit;
 }
 
-// merge split-KV partials and reduce MSE.  one CTA per head; thread = (row, dim-slice)
+// merge split-KV partials and reduce the squared error.  grid (BH, kCombineParts): block (bh, p) handles
+// the sampled rows r with r % kCombineParts == p and writes one partial sum per mask; a second tiny kernel
+// adds the partials in a fixed order (deterministic).
+constexpr int kCombineParts = 8;
+
 __global__ void __launch_bounds__(256)
 smse_combine_kernel(const float* __restrict__ o_part, const float* __restrict__ lse_part, int nsplit,
-                    int n_rows, int D, int BH, float* __restrict__ mse) {
-  // o_part: [3][BH][nsplit*128][D]; lse_part: [3][BH][nsplit*128]
-  const int bh = blockIdx.x;
+                    int n_rows, int D, int BH, float* __restrict__ partial) {
+  // o_part: [3][BH][nsplit*128][D]; lse_part: [3][BH][nsplit*128]; partial: [2][BH][kCombineParts]
+  const int bh = blockIdx.x, part = blockIdx.y;
   const size_t rows_per_head = static_cast<size_t>(nsplit) * 128;
   const size_t var_stride_o = static_cast<size_t>(BH) * rows_per_head * D;
   const size_t var_stride_l = static_cast<size_t>(BH) * rows_per_head;
   __shared__ float red[2][8];
   float acc0 = 0.f, acc1 = 0.f;
-  for (int e = threadIdx.x; e < n_rows * D; e += blockDim.x) {
-    const int r = e / D, d = e - r * D;
+  const int my_rows = (n_rows - part + kCombineParts - 1) / kCombineParts;
+  for (int e = threadIdx.x; e < my_rows * D; e += blockDim.x) {
+    const int r = part + (e / D) * kCombineParts, d = e % D;
     float outv[3];
 #pragma unroll
     for (int var = 0; var < 3; ++var) {
@@ -94,20 +99,28 @@ smse_combine_kernel(const float* __restrict__ o_part, const float* __restrict__ 
       a += red[0][w];
       b += red[1][w];
     }
-    const float n = static_cast<float>(n_rows) * D;
-    mse[bh] = a / n;
-    mse[BH + bh] = b / n;
+    partial[(0 * BH + bh) * kCombineParts + part] = a;
+    partial[(1 * BH + bh) * kCombineParts + part] = b;
   }
+}
+
+__global__ void smse_final_kernel(const float* __restrict__ partial, int BH, int n_rows, int D, float* __restrict__ mse) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // (mask, bh)
+  if (i >= 2 * BH) return;
+  float s = 0.f;
+  for (int p = 0; p < kCombineParts; ++p) s += partial[i * kCombineParts + p];
+  mse[i] = s / (static_cast<float>(n_rows) * D);
 }
 
 struct SmseLayout {
   int nsplit, n_chunks;
-  size_t qg, qidx, counts, items, chunks_plain, chunks_elem, o_part, lse_part, total;
+  size_t qg, qidx, counts, items, chunks_plain, chunks_elem, o_part, lse_part, partial, total;
 };
 static SmseLayout smse_layout(int BH, int S, int D) {
   SmseLayout L;
   L.n_chunks = (S + kChunkCols - 1) / kChunkCols;
   L.nsplit = 148 / BH;  // one wave: BH * nsplit <= number of SMs
+  if (L.nsplit > 32) L.nsplit = 32;  // few heads (per-head pipelines): keep the merge cheap
   if (L.nsplit > L.n_chunks) L.nsplit = L.n_chunks;
   if (L.nsplit < 1) L.nsplit = 1;
   size_t o = 0;
@@ -125,6 +138,7 @@ static SmseLayout smse_layout(int BH, int S, int D) {
   L.chunks_elem = take(sizeof(int2) * L.n_chunks);
   L.o_part = take(4ull * 3 * BH * rows * D);
   L.lse_part = take(4ull * 3 * BH * rows);
+  L.partial = take(4ull * 2 * BH * kCombineParts);
   L.total = o;
   return L;
 }
@@ -200,9 +214,12 @@ int svgb_sample_mse(const void* q, const void* k, const void* v, const int32_t* 
                       static_cast<long long>(S) * D, dtype, BH, D, a, L.nsplit, st))
       return -1;
   }
-  smse_combine_kernel<<<BH, 256, 0, st>>>(reinterpret_cast<const float*>(w + L.o_part),
-                                          reinterpret_cast<const float*>(w + L.lse_part), L.nsplit, n_rows, D,
-                                          BH, mse);
+  smse_combine_kernel<<<dim3(BH, kCombineParts), 256, 0, st>>>(
+      reinterpret_cast<const float*>(w + L.o_part), reinterpret_cast<const float*>(w + L.lse_part), L.nsplit,
+      n_rows, D, BH, reinterpret_cast<float*>(w + L.partial));
+  SVGB_LAUNCH_OK();
+  smse_final_kernel<<<(2 * BH + 127) / 128, 128, 0, st>>>(reinterpret_cast<const float*>(w + L.partial), BH, n_rows,
+                                                           D, mse);
   SVGB_LAUNCH_OK();
   return 0;
 }

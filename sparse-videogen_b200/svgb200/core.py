@@ -364,7 +364,7 @@ def sample_mse(q, k, v, rows, layout, ctx, F, P):
     check(lib().svgb_sample_mse(q.contiguous().data_ptr(), k.contiguous().data_ptr(), v.contiguous().data_ptr(),
                                 r.data_ptr(), n, BH, S, D, _dt(q), int(layout), ctx, F, P, out.data_ptr(),
                                 ws.data_ptr(), ws.numel(), _stream(q)), "svgb_sample_mse")
-    _bump(6)
+    _bump(7)
     return out
 
 

@@ -104,3 +104,41 @@ ms = t(lambda: core.attn_fwd(qp, kp, vp, plan, o_rows=sap.last["q_sorted_indices
 fl = 4.0 * D * (sap.last["q_sizes"].double()[:, :, None] * sap.last["k_sizes"].double()[:, None, :]
                 * sap.last["dynamic_map"]).sum().item()
 emit(stage="svg2.attention_on_kmeans_map", ms=ms, tflops=fl / ms / 1e9, density=fl / (4.0 * D * H * S * S))
+
+# ---- Wan 2.1 720p shape (BASELINE config 2: H=40, S=75600 = 21 x 3600, no text), SVG2: QC=300 / KC=1000
+del qq, kk, v, qp, kp, vp, plan, sap
+torch.cuda.empty_cache()
+from svgb200.models import wan  # noqa: E402
+
+Hw, Fw, Pw = 40, 21, 3600
+Sw = Fw * Pw
+gw = torch.Generator(device=dev).manual_seed(1)
+centw = torch.randn(Hw, 1000, D, device=dev, generator=gw) * 2
+labw = torch.randint(0, 1000, (Hw, Sw), device=dev, generator=gw)
+kw = (torch.gather(centw, 1, labw[:, :, None].expand(-1, -1, D)) + 0.5 * torch.randn(Hw, Sw, D, device=dev, generator=gw)).bfloat16()[None]
+qw = kw.clone()
+vw = torch.randn(1, Hw, Sw, D, device=dev, generator=gw).bfloat16()
+del centw, labw
+sapw = wan.WanSAPCore(Fw, Pw, num_q_centroids=300, num_k_centroids=1000, top_p_kmeans=0.9, min_kc_ratio=0.1,
+                      kmeans_iter_init=50, kmeans_iter_step=2)
+emit(stage="wan.sap_core_first_call(50it)", ms=t(lambda: sapw.sparse_core(qw, kw, vw), warm=0, iters=1))
+emit(stage="wan.sap_core_step_call(2it)", ms=t(lambda: sapw.sparse_core(qw, kw, vw), warm=0, iters=2))
+dw = core.density(sapw.last["dynamic_map"], sapw.last["q_sizes"], sapw.last["k_sizes"])
+planw = core.plan_varblock(sapw.last["dynamic_map"], sapw.last["q_sizes"], sapw.last["k_sizes"], Sw)
+qpw = core.permute_gather(qw, sapw.last["q_sorted_indices"])
+kpw = core.permute_gather(kw, sapw.last["k_sorted_indices"])
+vpw = core.permute_gather(vw, sapw.last["k_sorted_indices"])
+ms = t(lambda: core.attn_fwd(qpw, kpw, vpw, planw, o_rows=sapw.last["q_sorted_indices"]))
+flw = 4.0 * D * (sapw.last["q_sizes"].double()[:, :, None] * sapw.last["k_sizes"].double()[:, None, :]
+                 * sapw.last["dynamic_map"]).sum().item()
+emit(stage="wan.attention_on_kmeans_map", ms=ms, tflops=flw / ms / 1e9, density=float(dw.mean()))
+svg1w = wan.WanSVG1Core(Fw, Pw, Hw, D, 0.30, dev)
+rows = torch.randint(0, 10000, (64,))
+emit(stage="wan.svg1_sparse_core_total", ms=t(lambda: svg1w.sparse_core(qw, kw, vw, rows)))
+W_w = svg1w.block_mask.m2
+qi = torch.arange(Sw, dtype=torch.int64)
+lo = torch.clamp(qi - W_w, min=Pw)
+hi = torch.clamp(qi + W_w, max=Sw - 1)
+pairs_w = (torch.clamp(hi - lo + 1, min=0) + Pw).sum().item()   # band outside the first frame + first-frame sink
+ms = t(lambda: core.attn_fwd(qw, kw, vw, svg1w.block_mask.plan))
+emit(stage="wan.svg1_band_attention", ms=ms, W=W_w, tflops=4.0 * D * pairs_w * Hw / ms / 1e9, density=pairs_w / Sw / Sw)
