@@ -28,6 +28,7 @@ extern "C" {
 #define SVGB_BF16 0
 #define SVGB_F16 1
 #define SVGB_E4M3 2 /* fp8 e4m3 inputs (svgb_attn_fwd_fp8 only) */
+#define SVGB_F32 3  /* fp32 storage (transformer-block glue ops only) */
 
 /* element-mask families for the SVG1 band plan (reference generate_temporal_head_mask_mod) */
 #define SVGB_MASK_NONE 0
@@ -188,6 +189,61 @@ int svgb_sample_mse_bytes(int BH, int S, int D, int n_rows, size_t* bytes);
 int svgb_sample_mse(const void* q, const void* k, const void* v, const int32_t* rows, int n_rows,
                     int BH, int S, int D, int dtype, int layout, int ctx, int F, int P, float* mse,
                     void* ws, size_t ws_bytes, void* stream);
+
+/* ---- pre-attention elementwise chain (the reference's native `_kernels` module) ------- */
+/* rms_norm_forward (svg/kernels/csrc/ops.h:52-75): in place on x [m, n] 16-bit, gamma [n]; n in
+ * {32,64,128,256}; y = x * rsqrt(mean(x^2) + eps) * gamma, fp32 inside, one rounding. */
+int svgb_rms_norm(void* x, const void* gamma, long long m, int n, float eps, int dtype, void* stream);
+/* layer_norm_forward (ops.h:20-44): in place, eps fixed at 1e-5 like the reference kernel. */
+int svgb_layer_norm(void* x, const void* gamma, const void* beta, long long m, int n, int dtype, void* stream);
+/* apply_qk_rope_inplace_cossin{,_txtlast,_complex} (ops.h:77-260): q [B,Hq,S,D], k [B,Hk,S,D] 16-bit,
+ * rotated in place on S - len_text rows of every head; interleaved pairs (2i, 2i+1).
+ *   SVGB_ROPE_TXT_FIRST          skip the FIRST len_text rows; cos/sin float [S-len_text, D]
+ *   SVGB_ROPE_TXT_LAST           skip the LAST  len_text rows; cos/sin float [S-len_text, D]
+ *   SVGB_ROPE_COMPLEX_TXT_FIRST  cos/sin float [S-len_text, D/2] (real / imaginary parts), fp64 arithmetic */
+#define SVGB_ROPE_TXT_FIRST 0
+#define SVGB_ROPE_TXT_LAST 1
+#define SVGB_ROPE_COMPLEX_TXT_FIRST 2
+int svgb_qk_rope(void* q, void* k, const float* cos_t, const float* sin_t, int B, int Hq, int Hk, int S, int D,
+                 int len_text, int mode, int dtype, void* stream);
+/* The whole reference chain in one pass (hyvideo/attention.py:253-295, wan/attention.py:100-135):
+ *   q_in,k_in,v_in [B, S_in, H*D] (projection outputs; element strides given, so a packed QKV works)
+ *   -> unflatten + transpose + contiguous -> QK norm -> RoPE -> rows [out_row0, out_row0+S_in) of
+ *   q_out,k_out,v_out [B, H, S_out, D] (so the video and prompt streams of a double block land in one
+ *   tensor without torch.cat).  V is only transposed.
+ * norm: SVGB_NORM_NONE | SVGB_NORM_RMS_HEAD (gamma [D]) | SVGB_NORM_LAYER (gamma,beta [D], eps 1e-5) |
+ *       SVGB_NORM_RMS_HIDDEN (gamma [H*D]: RMS over the full hidden row before the head split, Wan).
+ * rope: 0 none | 1 cos/sin float [rope_n, D] | 2 complex float [rope_n, D/2]; tokens
+ *       [rope_lo, rope_lo+rope_n) of this input are rotated with table row (token - rope_lo).
+ * The norm result is rounded to the 16-bit dtype before RoPE, exactly like the in-place sequence. */
+#define SVGB_NORM_NONE 0
+#define SVGB_NORM_RMS_HEAD 1
+#define SVGB_NORM_LAYER 2
+#define SVGB_NORM_RMS_HIDDEN 3
+int svgb_qkv_prep(const void* q_in, const void* k_in, const void* v_in, long long in_token_stride,
+                  long long in_batch_stride, void* q_out, void* k_out, void* v_out, long long out_head_stride,
+                  long long out_batch_stride, int B, int S_in, int H, int D, int out_row0, int norm,
+                  const void* gamma_q, const void* gamma_k, const void* beta_q, const void* beta_k, float eps,
+                  int rope, const float* cos_t, const float* sin_t, int rope_lo, int rope_n, int dtype,
+                  void* stream);
+
+/* ---- Wan transformer-block glue (svg/kernels/triton/{layernorm,modulate,rmsnorm}.py) ---- */
+/* rows of N elements (N % 8 == 0, N <= 8192), contiguous; x/y/w dtypes: SVGB_BF16 | SVGB_F16 | SVGB_F32;
+ * scale/shift/gate are float [nb, N], row r uses vector r / rows_per_batch (rows_per_batch = 0: one vector). */
+/* y = LayerNorm(x) [* w + b] [* (1 + scale) + shift]: triton_layernorm_forward followed by
+ * triton_modulate_shift_forward (custom_models.py:37-56) in one pass; w/b and scale/shift optional. */
+int svgb_layernorm_modulate(const void* x, int x_dtype, const void* w, const void* b, int w_dtype, float eps,
+                            const float* scale, const float* shift, long long rows_per_batch, void* y, int y_dtype,
+                            long long rows, int N, void* stream);
+/* y = x * rsqrt(mean(x^2) + eps) * w over the full row (triton_rmsnorm_forward) */
+int svgb_rmsnorm_hidden(const void* x, int x_dtype, const void* w, int w_dtype, float eps, void* y, int y_dtype,
+                        long long rows, int N, void* stream);
+/* y = x * (1 + scale) + shift (triton_modulate_shift_forward) */
+int svgb_modulate_shift(const void* x, int x_dtype, const float* scale, const float* shift,
+                        long long rows_per_batch, void* y, int y_dtype, long long rows, int N, void* stream);
+/* y = residual + x * gate (triton_modulate_gate_residual_forward) */
+int svgb_gate_residual(const void* residual, int res_dtype, const void* x, int x_dtype, const float* gate,
+                       long long rows_per_batch, void* y, int y_dtype, long long rows, int N, void* stream);
 
 /* ---- self tests (debug; exercised by tests/ on the GPU) ----------------------------------- */
 /* One 128x128xD tile through the exact descriptor paths the attention kernel uses:

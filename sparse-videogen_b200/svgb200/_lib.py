@@ -59,6 +59,15 @@ _PROTOS = {
     "svgb_dynamic_map": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _i, _vp, _vp],
     "svgb_sample_mse_bytes": [_i, _i, _i, _i, _psz],
     "svgb_sample_mse": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _sz, _vp],
+    "svgb_rms_norm": [_vp, _vp, _ll, _i, _f, _i, _vp],
+    "svgb_layer_norm": [_vp, _vp, _vp, _ll, _i, _i, _vp],
+    "svgb_qk_rope": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
+    "svgb_qkv_prep": [_vp, _vp, _vp, _ll, _ll, _vp, _vp, _vp, _ll, _ll, _i, _i, _i, _i, _i, _i,
+                      _vp, _vp, _vp, _vp, _f, _i, _vp, _vp, _i, _i, _i, _vp],
+    "svgb_layernorm_modulate": [_vp, _i, _vp, _vp, _i, _f, _vp, _vp, _ll, _vp, _i, _ll, _i, _vp],
+    "svgb_rmsnorm_hidden": [_vp, _i, _vp, _i, _f, _vp, _i, _ll, _i, _vp],
+    "svgb_modulate_shift": [_vp, _i, _vp, _vp, _ll, _vp, _i, _ll, _i, _vp],
+    "svgb_gate_residual": [_vp, _i, _vp, _i, _vp, _ll, _vp, _i, _ll, _i, _vp],
     "svgb_selftest_tile": [_vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp],
 }
 

@@ -378,3 +378,193 @@ def selftest_tile(q, k, v, p_scale=0.0625):
                                    D, _dt(q), p_scale, _stream(q)), "svgb_selftest_tile")
     _bump()
     return s, o
+
+
+# ---- pre-attention chain (include/svgb200.h: svgb_rms_norm / svgb_layer_norm / svgb_qk_rope / svgb_qkv_prep)
+ROPE_TXT_FIRST, ROPE_TXT_LAST, ROPE_COMPLEX_TXT_FIRST = 0, 1, 2
+NORM_NONE, NORM_RMS_HEAD, NORM_LAYER, NORM_RMS_HIDDEN = 0, 1, 2, 3
+
+
+def _dt3(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return 3
+    return _dt(t)
+
+
+def _contig(*ts):
+    for t in ts:
+        if t is not None and not t.is_contiguous():
+            raise SvgbError("tensor must be contiguous")
+
+
+def rms_norm_(x: torch.Tensor, gamma: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
+    """In place on x [m, n] (any leading shape; last dim n in {32,64,128,256})."""
+    _need_cuda(x, gamma)
+    _contig(x, gamma)
+    if gamma.dim() != 1 or gamma.shape[0] != x.shape[-1] or gamma.dtype != x.dtype:
+        raise SvgbError("gamma must be [n] with the dtype of x")
+    n = x.shape[-1]
+    check(lib().svgb_rms_norm(x.data_ptr(), gamma.data_ptr(), x.numel() // n, n, float(eps), _dt(x), _stream(x)),
+          "svgb_rms_norm")
+    _bump()
+    return x
+
+
+def layer_norm_(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor) -> torch.Tensor:
+    _need_cuda(x, gamma, beta)
+    _contig(x, gamma, beta)
+    n = x.shape[-1]
+    if gamma.shape != (n,) or beta.shape != (n,) or gamma.dtype != x.dtype or beta.dtype != x.dtype:
+        raise SvgbError("gamma / beta must be [n] with the dtype of x")
+    check(lib().svgb_layer_norm(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), x.numel() // n, n, _dt(x),
+                                _stream(x)), "svgb_layer_norm")
+    _bump()
+    return x
+
+
+def qk_rope_(q: torch.Tensor, k: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor, len_text: int, mode: int):
+    """In place on q [B,Hq,S,D], k [B,Hk,S,D]; cos/sin float32 [S-len_text, D] (or [.., D/2] for the complex mode)."""
+    _need_cuda(q, k, cos, sin)
+    _contig(q, k, cos, sin)
+    if q.dim() != 4 or k.dim() != 4 or cos.dim() != 2 or sin.dim() != 2:
+        raise SvgbError("q, k must be 4-D and cos, sin 2-D")
+    if cos.dtype != torch.float32 or sin.dtype != torch.float32:
+        raise SvgbError("cos / sin caches must be float32")
+    B, Hq, S, D = q.shape
+    if k.shape[0] != B or k.shape[2] != S or k.shape[3] != D or k.dtype != q.dtype:
+        raise SvgbError("q and k must agree in batch, sequence, head_dim and dtype")
+    valid = S - int(len_text)
+    width = D // 2 if mode == ROPE_COMPLEX_TXT_FIRST else D
+    if tuple(cos.shape) != (valid, width) or tuple(sin.shape) != (valid, width):
+        raise SvgbError(f"cos / sin must be [{valid}, {width}], got {tuple(cos.shape)} / {tuple(sin.shape)}")
+    check(lib().svgb_qk_rope(q.data_ptr(), k.data_ptr(), cos.data_ptr(), sin.data_ptr(), B, Hq, k.shape[1], S, D,
+                             int(len_text), int(mode), _dt(q), _stream(q)), "svgb_qk_rope")
+    _bump()
+    return q, k
+
+
+def qkv_prep(q_in, k_in, v_in, heads: int, *, out=None, out_row0: int = 0, out_rows: Optional[int] = None,
+             norm: int = NORM_NONE, gamma_q=None, gamma_k=None, beta_q=None, beta_k=None, eps: float = 1e-6,
+             rope: int = 0, cos=None, sin=None, rope_lo: int = 0, rope_n: Optional[int] = None):
+    """[B, S_in, H*D] x3 -> (q, k, v) [B, H, S_out, D] rows [out_row0, out_row0+S_in) in one pass (transpose + QK norm
+    + RoPE).  q_in/k_in/v_in may be views of one packed projection (last dim contiguous)."""
+    _need_cuda(q_in, k_in, v_in, gamma_q, gamma_k, beta_q, beta_k, cos, sin)
+    B, S_in, HD = q_in.shape
+    D = HD // heads
+    for t in (q_in, k_in, v_in):
+        if t.shape != q_in.shape or t.dtype != q_in.dtype or t.stride(2) != 1 or t.stride() != q_in.stride():
+            raise SvgbError("q_in, k_in, v_in must share shape, dtype and strides (last dim contiguous)")
+    S_out = out_rows if out_rows is not None else (out[0].shape[2] if out is not None else S_in)
+    if out is None:
+        out = tuple(torch.empty(B, heads, S_out, D, dtype=q_in.dtype, device=q_in.device) for _ in range(3))
+    for t in out:
+        if tuple(t.shape) != (B, heads, S_out, D) or not t.is_contiguous() or t.dtype != q_in.dtype:
+            raise SvgbError("outputs must be contiguous [B, H, S_out, D] of the input dtype")
+    if out_row0 + S_in > S_out:
+        raise SvgbError("out_row0 + S_in exceeds the output rows")
+    if rope:
+        if cos is None or sin is None or cos.dtype != torch.float32 or sin.dtype != torch.float32:
+            raise SvgbError("rope needs float32 cos / sin tables")
+        _contig(cos, sin)
+        if rope_n is None:
+            rope_n = cos.shape[0]
+        width = D // 2 if rope == 2 else D
+        if tuple(cos.shape) != (rope_n, width) or tuple(sin.shape) != (rope_n, width):
+            raise SvgbError(f"cos / sin must be [{rope_n}, {width}]")
+    else:
+        rope_n = 0
+    for g, n in ((gamma_q, "gamma_q"), (gamma_k, "gamma_k"), (beta_q, "beta_q"), (beta_k, "beta_k")):
+        if g is not None:
+            want = HD if norm == NORM_RMS_HIDDEN else D
+            if g.dtype != q_in.dtype or g.numel() != want or not g.is_contiguous():
+                raise SvgbError(f"{n} must be contiguous [{want}] of the input dtype")
+    check(lib().svgb_qkv_prep(q_in.data_ptr(), k_in.data_ptr(), v_in.data_ptr(), q_in.stride(1), q_in.stride(0),
+                              out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(), S_out * D, heads * S_out * D,
+                              B, S_in, heads, D, int(out_row0), int(norm), _p(gamma_q), _p(gamma_k), _p(beta_q),
+                              _p(beta_k), float(eps), int(rope), _p(cos), _p(sin), int(rope_lo), int(rope_n),
+                              _dt(q_in), _stream(q_in)), "svgb_qkv_prep")
+    _bump()
+    return out
+
+
+# ---- Wan transformer-block glue (svgb_layernorm_modulate / svgb_rmsnorm_hidden / svgb_modulate_shift / svgb_gate_residual)
+_TORCH_DT = {torch.bfloat16: 0, torch.float16: 1, torch.float32: 3}
+
+
+def _mod_vec(v, N):
+    """scale / shift / gate: float32 [N], [nb, N] or [nb, 1, N] -> (tensor [nb, N], nb)."""
+    if v.dtype != torch.float32:
+        raise SvgbError("modulation vectors must be float32")
+    v = v.reshape(-1, N)
+    _contig(v)
+    return v, v.shape[0]
+
+
+def _rows_per_batch(rows, nb):
+    if nb == 1:
+        return 0
+    if rows % nb:
+        raise SvgbError("rows not divisible by the number of modulation vectors")
+    return rows // nb
+
+
+def layernorm_modulate(x, weight=None, bias=None, eps=1e-6, scale=None, shift=None, out_dtype=None):
+    _need_cuda(x, weight, bias, scale, shift)
+    _contig(x, weight, bias)
+    N = x.shape[-1]
+    rows = x.numel() // N
+    rpb = 0
+    if scale is not None:
+        scale, nb = _mod_vec(scale, N)
+        shift, nb2 = _mod_vec(shift, N)
+        if nb != nb2:
+            raise SvgbError("scale and shift must have the same batch")
+        rpb = _rows_per_batch(rows, nb)
+    y = torch.empty(x.shape, dtype=out_dtype or torch.float32, device=x.device)
+    check(lib().svgb_layernorm_modulate(x.data_ptr(), _dt3(x), _p(weight), _p(bias),
+                                        _dt3(weight) if weight is not None else 0, float(eps), _p(scale), _p(shift),
+                                        rpb, y.data_ptr(), _TORCH_DT[y.dtype], rows, N, _stream(x)),
+          "svgb_layernorm_modulate")
+    _bump()
+    return y
+
+
+def rmsnorm_hidden(x, weight, eps, out_dtype=None):
+    _need_cuda(x, weight)
+    _contig(x, weight)
+    N = x.shape[-1]
+    y = torch.empty(x.shape, dtype=out_dtype or x.dtype, device=x.device)
+    check(lib().svgb_rmsnorm_hidden(x.data_ptr(), _dt3(x), weight.data_ptr(), _dt3(weight), float(eps), y.data_ptr(),
+                                    _TORCH_DT[y.dtype], x.numel() // N, N, _stream(x)), "svgb_rmsnorm_hidden")
+    _bump()
+    return y
+
+
+def modulate_shift(x, scale, shift, out_dtype=torch.float32):
+    _need_cuda(x, scale, shift)
+    _contig(x)
+    N = x.shape[-1]
+    rows = x.numel() // N
+    scale, nb = _mod_vec(scale, N)
+    shift, _ = _mod_vec(shift, N)
+    y = torch.empty(x.shape, dtype=out_dtype, device=x.device)
+    check(lib().svgb_modulate_shift(x.data_ptr(), _dt3(x), scale.data_ptr(), shift.data_ptr(), _rows_per_batch(rows, nb),
+                                    y.data_ptr(), _TORCH_DT[y.dtype], rows, N, _stream(x)), "svgb_modulate_shift")
+    _bump()
+    return y
+
+
+def gate_residual(residual, x, gate, out_dtype=torch.float32):
+    _need_cuda(residual, x, gate)
+    _contig(residual, x)
+    if residual.shape != x.shape:
+        raise SvgbError("residual and x must have the same shape")
+    N = x.shape[-1]
+    rows = x.numel() // N
+    gate, nb = _mod_vec(gate, N)
+    y = torch.empty(x.shape, dtype=out_dtype, device=x.device)
+    check(lib().svgb_gate_residual(residual.data_ptr(), _dt3(residual), x.data_ptr(), _dt3(x), gate.data_ptr(),
+                                   _rows_per_batch(rows, nb), y.data_ptr(), _TORCH_DT[y.dtype], rows, N, _stream(x)),
+          "svgb_gate_residual")
+    _bump()
+    return y

@@ -9,6 +9,7 @@ from typing import Optional
 import torch
 
 from .. import core
+from ..timer import time_logging_decorator
 from ..kmeans_utils import batch_kmeans_Euclid
 
 
@@ -117,21 +118,26 @@ class SVG1Core:
 
     # -- the sparse branch ---------------------------------------------------------------------------
     def sparse_core(self, query, key, value, sampled_rows=None, attn_events=None):
-        sampled_mses = self.sample_mse(query, key, value, sampled_rows)
-        best_mask_idx = torch.argmin(sampled_mses, dim=0)  # ties -> 0 (spatial), like the reference (:508)
-        q_out, k_out, v_out = torch.empty_like(query), torch.empty_like(key), torch.empty_like(value)
-        self.fast_sparse_head_placement(query, key, value, q_out, k_out, v_out, best_mask_idx, self.context_length,
-                                        self.num_frame, self.frame_size)
+        # stage labels = the reference's TIME_BENCH table (hyvideo/attention.py:375,401,405,439)
+        with time_logging_decorator("Level 3 - sample mse"):
+            sampled_mses = self.sample_mse(query, key, value, sampled_rows)
+            best_mask_idx = torch.argmin(sampled_mses, dim=0)  # ties -> 0 (spatial), like the reference (:508)
+        with time_logging_decorator("Level 3 - fast sparse head placement"):
+            q_out, k_out, v_out = torch.empty_like(query), torch.empty_like(key), torch.empty_like(value)
+            self.fast_sparse_head_placement(query, key, value, q_out, k_out, v_out, best_mask_idx,
+                                            self.context_length, self.num_frame, self.frame_size)
         if attn_events is not None:
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
-        hidden = self.sparse_flex_attention(q_out, k_out, v_out, self.block_mask)
+        with time_logging_decorator("Level 3 - sparse flex attention"):
+            hidden = self.sparse_flex_attention(q_out, k_out, v_out, self.block_mask)
         if attn_events is not None:
             b.record()
             attn_events.append((a, b))
-        out = torch.empty_like(query)
-        self.fast_hidden_states_placement(hidden, out, best_mask_idx, self.context_length, self.num_frame,
-                                          self.frame_size)
+        with time_logging_decorator("Level 3 - fast hidden states placement"):
+            out = torch.empty_like(query)
+            self.fast_hidden_states_placement(hidden, out, best_mask_idx, self.context_length, self.num_frame,
+                                              self.frame_size)
         return out
 
     def sparse_core_head_parallel(self, query, key, value, hp, sampled_rows=None, out=None, attn_events=None):
@@ -223,7 +229,8 @@ class SVG1Core:
             cu = cu_max_seqlens[0]
             seg = (cu[1:] - cu[:-1]).tolist()
             seg = [s for s in seg if s > 0]
-        return dense_attention(query, key, value, seg)
+        with time_logging_decorator("Level 3 - Dense Flash Attention"):
+            return dense_attention(query, key, value, seg)
 
     def attention_core_logic(self, query, key, value, timestep, layer_idx=None, cu_max_seqlens=None):
         cfg, H, S, D = query.shape
@@ -245,9 +252,11 @@ class SAPCore:
 
     def __init__(self, context_length, num_frame, frame_size, num_q_centroids, num_k_centroids, top_p_kmeans,
                  min_kc_ratio, kmeans_iter_init, kmeans_iter_step, prompt_length=0, zero_step_kmeans_init=False,
-                 first_layers_fp=0, first_times_fp=0, layer_idx=0, state: Optional[KMeansState] = None):
+                 first_layers_fp=0, first_times_fp=0, layer_idx=0, state: Optional[KMeansState] = None,
+                 logging_file: Optional[str] = None):
         self.context_length, self.num_frame, self.frame_size = context_length, num_frame, frame_size
         self.prompt_length = prompt_length
+        self.logging_file = logging_file  # density JSONL (hyvideo/attention.py:786-802); None = off
         self.num_q_centroids, self.num_k_centroids = num_q_centroids, num_k_centroids
         self.top_p_kmeans, self.min_kc_ratio = top_p_kmeans, min_kc_ratio
         self.kmeans_iter_init, self.kmeans_iter_step = kmeans_iter_init, kmeans_iter_step
@@ -262,7 +271,23 @@ class SAPCore:
                                   self.num_q_centroids, self.num_k_centroids, self.kmeans_iter_init,
                                   self.kmeans_iter_step)
 
-    def sparse_core(self, query, key, value, layer_idx=None):
+    def log_density(self, timestep, layer_idx, dyn_map, q_sizes, k_sizes):
+        """One JSON line per sparse call in the reference's schema (hyvideo/attention.py:786-802), read by
+        svg/utils/density.py and densities_get_mean.py: {"timestep", "layer", "avg_density", "density"}."""
+        import json
+
+        from ..kmeans_utils import density_calculation
+
+        H = dyn_map.shape[0]
+        densities = density_calculation(dyn_map[None], q_sizes.view(1, H, -1), k_sizes.view(1, H, -1))
+        t = timestep[0].item() if hasattr(timestep, "__getitem__") else timestep
+        entry = {"timestep": t, "layer": layer_idx, "avg_density": densities.mean().item(),
+                 "density": densities.tolist()}
+        with open(self.logging_file, "a") as f:
+            f.write(json.dumps(entry) + "\n")
+        return entry
+
+    def sparse_core(self, query, key, value, layer_idx=None, timestep=None):
         from ..kmeans_utils import identify_dynamic_map
 
         cfg, H, S, D = query.shape
@@ -272,7 +297,8 @@ class SAPCore:
         dev = query.device
         qv = query[:, :, :V].contiguous() if ctx else query
         kv = key[:, :, :V].contiguous() if ctx else key
-        ql, qc, qs, kl, kc, ks = self.kmeans_clustering(qv, kv, layer_idx)
+        with time_logging_decorator("Level 3.5 - kmeans clustering"):
+            ql, qc, qs, kl, kc, ks = self.kmeans_clustering(qv, kv, layer_idx)
         QC, KC = self.num_q_centroids, self.num_k_centroids
         dyn = identify_dynamic_map(qc.view(cfg, H, QC, D), kc.view(cfg, H, KC, D), qs.view(cfg, H, QC),
                                    ks.view(cfg, H, KC), self.top_p_kmeans, self.min_kc_ratio).view(H, QC, KC)
@@ -293,13 +319,18 @@ class SAPCore:
             extra = torch.tensor([self.prompt_length, unprompt], dtype=torch.int32, device=dev).expand(H, 2)
             row_sz = torch.cat([row_sz, extra], dim=1)
             col_sz = torch.cat([col_sz, extra], dim=1)
-        qp = core.permute_gather(query, q_perm)
-        kp = core.permute_gather(key, k_perm)
-        vp = core.permute_gather(value, k_perm)
-        plan = core.plan_varblock(dyn, row_sz, col_sz, S)
-        out = core.attn_fwd(qp, kp, vp, plan, o_rows=q_perm)  # inverse permutation fused into the store
+        with time_logging_decorator("Level 3 - semantic aware permutation"):
+            qp = core.permute_gather(query, q_perm)
+            kp = core.permute_gather(key, k_perm)
+            vp = core.permute_gather(value, k_perm)
+        with time_logging_decorator("Level 3 - sparse flashinfer attention"):
+            plan = core.plan_varblock(dyn, row_sz, col_sz, S)
+            out = core.attn_fwd(qp, kp, vp, plan, o_rows=q_perm)  # inverse permutation fused into the store
         self.last = {"dynamic_map": dyn, "q_sizes": row_sz, "k_sizes": col_sz, "q_sorted_indices": q_perm,
                      "k_sorted_indices": k_perm}
+        if self.logging_file is not None:
+            with time_logging_decorator("Level 3 - density calculation and logging"):
+                self.log_density(0 if timestep is None else timestep, layer_idx, dyn, row_sz, col_sz)
         return out
 
     def attention_core_logic(self, query, key, value, timestep, layer_idx=None, cu_max_seqlens=None):
@@ -316,4 +347,4 @@ class SAPCore:
                 cu = cu_max_seqlens[0]
                 seg = [s for s in (cu[1:] - cu[:-1]).tolist() if s > 0]
             return dense_attention(query, key, value, seg)
-        return self.sparse_core(query, key, value, layer_idx)
+        return self.sparse_core(query, key, value, layer_idx, timestep)

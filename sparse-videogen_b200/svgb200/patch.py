@@ -53,3 +53,27 @@ def install_kmeans_utils(module=None) -> list:
     for n in names:
         setattr(module, n, getattr(_ku, n))
     return names
+
+
+def install_native_kernels() -> None:
+    """Make `import _kernels` (svg/models/*/attention.py: `sys.path.append("svg/kernels/build/"); import _kernels`)
+    resolve to the svgb200 implementation, so the reference's ENABLE_FAST_KERNEL branch runs these kernels."""
+    import sys
+
+    from . import _kernels as k
+
+    sys.modules["_kernels"] = k
+
+
+def install_triton_glue(module) -> list:
+    """Replace the Triton glue names a reference module imported (svg/models/wan/custom_models.py:16-17,
+    svg/models/wan/attention.py:16)."""
+    from . import triton_glue as g
+
+    done = []
+    for name in ("triton_rmsnorm_forward", "triton_layernorm_forward", "triton_modulate_shift_forward",
+                 "triton_modulate_gate_residual_forward"):
+        if hasattr(module, name):
+            setattr(module, name, getattr(g, name))
+            done.append(name)
+    return done
