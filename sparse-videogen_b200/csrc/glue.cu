@@ -96,43 +96,6 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
   return r;
 }
 
-// merge (count, mean, M2) of two disjoint sets (Chan et al.)
-__device__ __forceinline__ void merge_stats(float& n, float& mu, float& m2, float nb, float mub, float m2b) {
-  const float nt = n + nb;
-  if (nt > 0.f) {
-    const float d = mub - mu, w = nb / nt;
-    mu += d * w;
-    m2 += m2b + d * d * n * w;
-    n = nt;
-  }
-}
-// block-wide merge; every thread returns the same totals (fixed order)
-__device__ __forceinline__ void block_merge_stats(float& n, float& mu, float& m2, float (*st)[kGlueThreads / 32]) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const float nb = __shfl_xor_sync(0xffffffffu, n, o);
-    const float mub = __shfl_xor_sync(0xffffffffu, mu, o);
-    const float m2b = __shfl_xor_sync(0xffffffffu, m2, o);
-    // both partners must compute the same merged value: order the pair by lane
-    if ((threadIdx.x & o) == 0) merge_stats(n, mu, m2, nb, mub, m2b);
-    else {
-      float n2 = nb, mu2 = mub, m22 = m2b;
-      merge_stats(n2, mu2, m22, n, mu, m2);
-      n = n2; mu = mu2; m2 = m22;
-    }
-  }
-  __syncthreads();  // st[] may still be read from the previous row
-  if ((threadIdx.x & 31) == 0) {
-    st[0][threadIdx.x >> 5] = n;
-    st[1][threadIdx.x >> 5] = mu;
-    st[2][threadIdx.x >> 5] = m2;
-  }
-  __syncthreads();
-  n = st[0][0]; mu = st[1][0]; m2 = st[2][0];
-#pragma unroll
-  for (int w = 1; w < kGlueThreads / 32; ++w) merge_stats(n, mu, m2, st[0][w], st[1][w], st[2][w]);
-}
-
 struct GlueArgs {
   const void* x;
   const void* res;    // residual (gate_residual); same storage width as x
@@ -153,10 +116,9 @@ enum GlueOp { kOpLayerNorm = 0, kOpRmsNorm = 1, kOpModulate = 2, kOpGateResidual
 // kOpLayerNorm: y = LN(x)[*w + b][*(1+scale) + shift];  kOpRmsNorm: y = x * rstd * w
 // kOpModulate : y = x * (1+scale) + shift;              kOpGateResidual: y = res + x * gate
 template <int OP, bool F32, bool RF32>
-__global__ void __launch_bounds__(kGlueThreads, (F32 || RF32 || OP == 3) ? 1 : 4)
+__global__ void __launch_bounds__(kGlueThreads)
 glue_rows_kernel(const GlueArgs a) {
   __shared__ float red[kGlueThreads / 32];
-  __shared__ float stats[3][kGlueThreads / 32];
   constexpr bool kRes = OP == kOpGateResidual;
   const int nvec = a.N / 8;
   Raw8<F32> cur[kMaxVec], nxt[kMaxVec];
@@ -179,9 +141,7 @@ glue_rows_kernel(const GlueArgs a) {
     const long long mod_off = a.rows_per_batch > 0 ? (row / a.rows_per_batch) * a.N : 0;
     float mean = 0.f, rstd = 1.f;
     if constexpr (OP == kOpLayerNorm) {
-      // per-thread mean and centred sum of squares over its own elements (two passes over registers), then ONE
-      // block-wide pairwise merge of (count, mean, M2): mathematically the reference's mean / centred variance
-      float s = 0.f, cnt = 0.f;
+      float s = 0.f;
 #pragma unroll
       for (int j = 0; j < kMaxVec; ++j) {
         if (threadIdx.x + j * kGlueThreads < nvec) {
@@ -189,22 +149,20 @@ glue_rows_kernel(const GlueArgs a) {
           unpack_raw<F32>(cur[j], a.x_dtype, f);
 #pragma unroll
           for (int i = 0; i < 8; ++i) s += f[i];
-          cnt += 8.f;
         }
       }
-      float mu = cnt > 0.f ? s / cnt : 0.f, m2 = 0.f;
+      mean = block_sum(s, red) / a.N;
+      float ss = 0.f;
 #pragma unroll
       for (int j = 0; j < kMaxVec; ++j) {
         if (threadIdx.x + j * kGlueThreads < nvec) {
           float f[8];
           unpack_raw<F32>(cur[j], a.x_dtype, f);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) m2 += (f[i] - mu) * (f[i] - mu);
+          for (int i = 0; i < 8; ++i) ss += (f[i] - mean) * (f[i] - mean);
         }
       }
-      block_merge_stats(cnt, mu, m2, stats);
-      mean = mu;
-      rstd = 1.0f / sqrtf(m2 / a.N + a.eps);
+      rstd = 1.0f / sqrtf(block_sum(ss, red) / a.N + a.eps);
     } else if constexpr (OP == kOpRmsNorm) {
       float ss = 0.f;
 #pragma unroll
