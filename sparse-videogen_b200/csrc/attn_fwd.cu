@@ -585,3 +585,11 @@ int svgb_selftest_tile(const void* q, const void* k, const void* v, float* s_out
 }
 
 }  // extern "C"
+
+#ifdef SVGB_ATTN_TRACE
+extern "C" int svgb_debug_attn_trace(long long* host, int n) {
+  SVGB_CUDA(cudaDeviceSynchronize());
+  SVGB_CUDA(cudaMemcpyFromSymbol(host, svgb::g_attn_trace, sizeof(long long) * (n < 1536 ? n : 1536)));
+  return 0;
+}
+#endif

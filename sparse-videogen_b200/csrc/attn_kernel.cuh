@@ -60,10 +60,24 @@ struct AttnBars {
   uint64_t p_full[2];
   uint64_t kv_full[8];
   uint64_t kv_empty[8];
+  uint64_t pv_done;  // single-tile (ping-pong) items: completes once per PV
   uint32_t tmem_base;
   uint32_t pad_[3];
   float xch[2 * 2 * 128];  // row-max / row-sum exchange between the two halves of a row (double-buffered)
 };
+
+#ifdef SVGB_ATTN_TRACE
+// bring-up only: per-chunk clock64 timestamps of one CTA (item SVGB_ATTN_TRACE of head 0)
+__device__ long long g_attn_trace[3 * 64 * 8];
+#define SVGB_TRACE(role, j, ev)                                                                   \
+  do {                                                                                            \
+    if (trace_on && (j) < 64 && lane == 0) g_attn_trace[((role) * 64 + (j)) * 8 + (ev)] = clock64(); \
+  } while (0)
+#else
+#define SVGB_TRACE(role, j, ev) \
+  do {                          \
+  } while (0)
+#endif
 
 constexpr float kRescaleTau = 8.0f;  // log2 units
 // register budget per role (launch: 384 threads x 168): warps 0-3 give registers to the 8 softmax warps
@@ -108,6 +122,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+#ifdef SVGB_ATTN_TRACE
+  const bool trace_on = bh == 0 && blockIdx.x == SVGB_ATTN_TRACE && (warp == 1 || warp == 4 || warp == 8);
+#endif
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&qmap);
@@ -118,6 +135,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
     const uint32_t n_prod = gather ? 3u : 1u;  // gather: one arrival per producer warp (0, 2, 3)
     mbar_init(smem_u32(&bars->q_full), n_prod);
     mbar_init(smem_u32(&bars->o_final), 1);
+    mbar_init(smem_u32(&bars->pv_done), 1);
     for (int t = 0; t < 2; ++t) {
       mbar_init(smem_u32(&bars->s_full[t]), 1);
       mbar_init(smem_u32(&bars->p_full[t]), per_tile_map ? 128 : 256);
@@ -276,39 +294,133 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     setmaxnreg_dec<kRegsLight>();
-    if (lane == 0 && nchunks > 0) {
-      auto issue_qk = [&](int t, int slot, int ncols) {
-        const uint32_t idesc = FP8 ? make_idesc_e4m3(128, ncols, false, false)
-                                   : make_idesc(128, ncols, DT == DT_BF16, false, false);
-        const uint32_t d_tmem = tmem + (t == 0 ? Cfg::kSCol0 : Cfg::kSCol1);
+    if (nchunks > 0 && ntiles == 1) {
+      // ---- single-tile item: the two S buffers ping-pong over the CHUNK stream (even chunks -> S0, odd -> S1), both
+      // accumulate into O0.  QK(j+1) is in flight / done while the softmax of chunk j runs, PV(j) is issued as soon
+      // as P(j) is written, QK(j+2) follows it into the buffer it just consumed.  Ring order is unchanged
+      // (K(j) = entry 2j, V(j) = entry 2j+1).  pv_done completes once per PV: the lazy O rescale of chunk j waits
+      // for PV(j-1) on it.  (+28 % on all-single-tile plans, sample_mse 1.33 -> 1.05 ms per 12 heads.)
+      if (lane == 0) {
+        auto chunk_n = [&](int jj) -> int {
+          const int vld = gather ? min(kChunkCols, total_kv - jj * kChunkCols) : chunk_valid(__ldg(&chunks[jj].y));
+          return (vld + Cfg::kMmaK - 1) & ~(Cfg::kMmaK - 1);
+        };
+        auto issue_qk = [&](int sbuf, int slot, int ncols) {  // S[sbuf] = Q_0 K^T
+          const uint32_t idesc = FP8 ? make_idesc_e4m3(128, ncols, false, false)
+                                     : make_idesc(128, ncols, DT == DT_BF16, false, false);
+          const uint32_t d_tmem = tmem + (sbuf == 0 ? Cfg::kSCol0 : Cfg::kSCol1);
 #pragma unroll
-        for (int kk = 0; kk < Cfg::kRowBytes / 32; ++kk) {  // 32 bytes of the head dim per MMA
-          const uint32_t off = (kk >> 2) * Cfg::kPanelBytes + (kk & 3) * 32;
-          const uint64_t a = desc_kmajor_sw128(sQ + t * Cfg::kTileBytes + off);
-          const uint64_t b = desc_kmajor_sw128(sRing + slot * Cfg::kTileBytes + off);
-          if constexpr (FP8) mma_ss_f8(d_tmem, a, b, idesc, kk > 0 ? 1u : 0u);
-          else mma_ss(d_tmem, a, b, idesc, kk > 0 ? 1u : 0u);
+          for (int kk = 0; kk < Cfg::kRowBytes / 32; ++kk) {  // 32 bytes of the head dim per MMA
+            const uint32_t off = (kk >> 2) * Cfg::kPanelBytes + (kk & 3) * 32;
+            const uint64_t a = desc_kmajor_sw128(sQ + off);
+            const uint64_t b = desc_kmajor_sw128(sRing + slot * Cfg::kTileBytes + off);
+            if constexpr (FP8) mma_ss_f8(d_tmem, a, b, idesc, kk > 0 ? 1u : 0u);
+            else mma_ss(d_tmem, a, b, idesc, kk > 0 ? 1u : 0u);
+          }
+        };
+        auto issue_pv = [&](int sbuf, int slot, int ncols, bool acc) {  // O_0 += P[sbuf] V
+          const uint32_t idesc = FP8 ? make_idesc_e4m3(128, D, false, true) : make_idesc(128, D, DT == DT_BF16, false, true);
+          const uint32_t d_tmem = tmem + Cfg::kOCol0;
+          const uint32_t p_tmem = tmem + (sbuf == 0 ? Cfg::kSCol0 : Cfg::kSCol1);
+          const int nk = ncols / Cfg::kMmaK;
+          for (int kk = 0; kk < nk; ++kk) {
+            // kMmaK kv rows per MMA: kMmaK x 128 B down the V panel; P advances 8 TMEM columns (32 bytes).
+            const uint64_t b = desc_mnmajor_sw128(sRing + slot * Cfg::kTileBytes + kk * Cfg::kMmaK * 128, Cfg::kPanelBytes);
+            if constexpr (FP8) mma_ts_f8(d_tmem, p_tmem + kk * 8, b, idesc, (acc || kk > 0) ? 1u : 0u);
+            else mma_ts(d_tmem, p_tmem + kk * 8, b, idesc, (acc || kk > 0) ? 1u : 0u);
+          }
+        };
+        auto wait_full = [&](int idx) {
+          mbar_wait(smem_u32(&bars->kv_full[idx % kStages]), (idx / kStages) & 1, 3);
+          if constexpr (kGather) fence_proxy_async_smem();
+          tc_fence_after();
+        };
+        auto release = [&](int idx) { tc_commit(smem_u32(&bars->kv_empty[idx % kStages])); };
+        mbar_wait(smem_u32(&bars->q_full), 0, 2);
+        if constexpr (kGather) fence_proxy_async_smem();
+        for (int j = 0; j < 2 && j < nchunks; ++j) {
+          wait_full(2 * j);
+          issue_qk(j, (2 * j) % kStages, chunk_n(j));
+          tc_commit(smem_u32(&bars->s_full[j]));
+          release(2 * j);
         }
-      };
-      auto issue_pv = [&](int t, int slot, int ncols, bool acc) {
-        const uint32_t idesc = FP8 ? make_idesc_e4m3(128, D, false, true) : make_idesc(128, D, DT == DT_BF16, false, true);
-        const uint32_t d_tmem = tmem + (t == 0 ? Cfg::kOCol0 : Cfg::kOCol1);
-        const uint32_t p_tmem = tmem + (t == 0 ? Cfg::kSCol0 : Cfg::kSCol1);
-        const int nk = ncols / Cfg::kMmaK;
-        for (int kk = 0; kk < nk; ++kk) {
-          // kMmaK kv rows per MMA: kMmaK x 128 B down the V panel; P advances 8 TMEM columns (32 bytes).
-          const uint64_t b = desc_mnmajor_sw128(sRing + slot * Cfg::kTileBytes + kk * Cfg::kMmaK * 128, Cfg::kPanelBytes);
-          if constexpr (FP8) mma_ts_f8(d_tmem, p_tmem + kk * 8, b, idesc, (acc || kk > 0) ? 1u : 0u);
-          else mma_ts(d_tmem, p_tmem + kk * 8, b, idesc, (acc || kk > 0) ? 1u : 0u);
+        for (int j = 0; j < nchunks; ++j) {
+          const int b = j & 1;
+          wait_full(2 * j + 1);
+          mbar_wait(smem_u32(&bars->p_full[b]), (j >> 1) & 1, 5);
+          tc_fence_after();
+          issue_pv(b, (2 * j + 1) % kStages, chunk_n(j), j > 0);
+          release(2 * j + 1);
+          tc_commit(smem_u32(&bars->pv_done));
+          if (j + 2 < nchunks) {
+            wait_full(2 * j + 4);
+            issue_qk(b, (2 * j + 4) % kStages, chunk_n(j + 2));
+            tc_commit(smem_u32(&bars->s_full[b]));
+            release(2 * j + 4);
+          }
         }
-      };
+        tc_commit(smem_u32(&bars->o_final));
+      }
+    } else
+    // ---- two-tile items: streamed issue (elect.sync leader, running descriptors), so the tensor pipe runs at its
+    // 64 cycles per M=128,N=128,K=16 MMA instead of the ~90 cycles a rebuilt-descriptor loop can issue at
+    if (nchunks > 0 && elect_one()) {  // elect.sync: ptxas then knows a single lane runs the tcgen05 stream
       // MMA N of chunk jj: run-tail / band chunks carry it in the chunk list; gather chunks are all full
       // except the last
       auto chunk_n = [&](int jj) -> int {
         const int vld = gather ? min(kChunkCols, total_kv - jj * kChunkCols) : chunk_valid(__ldg(&chunks[jj].y));
         return (vld + Cfg::kMmaK - 1) & ~(Cfg::kMmaK - 1);
       };
-
+      // The issuing thread's own instruction stream must not pace the tensor pipe (one M=128,N=128,K=16 MMA is 64
+      // cycles of tensor time) nor sit between a barrier wait and the first MMA of a group.  Descriptors are
+      // therefore split into a constant high word and a running low word (address field, units of 16 B; all tiles
+      // live below 256 KB so the 14-bit field never carries): per MMA the stream is "add a constant, issue".  The
+      // empty asm after each MMA pins that order -- without it ptxas hoists all eight address computations (and
+      // their R2UR moves) in front of the first MMA, which puts ~60 scalar instructions on the softmax->MMA
+      // critical path.
+      auto lo32 = [](uint64_t d) { return static_cast<uint32_t>(d); };
+      auto hi32 = [](uint64_t d) { return static_cast<uint32_t>(d >> 32); };
+      auto mk64 = [](uint32_t lo, uint32_t hi) { return (static_cast<uint64_t>(hi) << 32) | lo; };
+      const uint32_t k_hi = hi32(desc_kmajor_sw128(sRing)), v_hi = hi32(desc_mnmajor_sw128(sRing, Cfg::kPanelBytes));
+      const uint32_t q_lo[2] = {lo32(desc_kmajor_sw128(sQ)), lo32(desc_kmajor_sw128(sQ + Cfg::kTileBytes))};
+      const uint32_t k_lo0 = lo32(desc_kmajor_sw128(sRing)), v_lo0 = lo32(desc_mnmajor_sw128(sRing, Cfg::kPanelBytes));
+      constexpr uint32_t kSlotStep = Cfg::kTileBytes >> 4;
+      auto qk_idesc = [&](int ncols) -> uint32_t {
+        return FP8 ? make_idesc_e4m3(128, ncols, false, false) : make_idesc(128, ncols, DT == DT_BF16, false, false);
+      };
+      // S_t = Q_t K^T; b_lo = low descriptor word of the K tile (k_lo0 + slot * kSlotStep)
+      auto issue_qk = [&](int t, uint32_t b_lo, uint32_t idesc) {
+        const uint32_t d_tmem = tmem + (t == 0 ? Cfg::kSCol0 : Cfg::kSCol1);
+        uint32_t a_lo = q_lo[t];
+#pragma unroll
+        for (int kk = 0; kk < Cfg::kRowBytes / 32; ++kk) {  // 32 bytes of the head dim per MMA
+          if constexpr (FP8) mma_ss_f8(d_tmem, mk64(a_lo, k_hi), mk64(b_lo, k_hi), idesc, kk > 0 ? 1u : 0u);
+          else mma_ss(d_tmem, mk64(a_lo, k_hi), mk64(b_lo, k_hi), idesc, kk > 0 ? 1u : 0u);
+          asm volatile("" : "+r"(a_lo), "+r"(b_lo));
+          // next 32-byte K step: +32 B inside a 128-byte panel row, then on to the next 16 KB panel
+          const uint32_t step = ((kk & 3) == 3) ? ((Cfg::kPanelBytes - 3 * 32) >> 4) : (32 >> 4);
+          a_lo += step;
+          b_lo += step;
+        }
+      };
+      // O_t += P_t V; b_lo = low descriptor word of the V tile (v_lo0 + slot * kSlotStep)
+      auto issue_pv = [&](int t, uint32_t b_lo, int ncols, bool acc) {
+        const uint32_t idesc = FP8 ? make_idesc_e4m3(128, D, false, true) : make_idesc(128, D, DT == DT_BF16, false, true);
+        const uint32_t d_tmem = tmem + (t == 0 ? Cfg::kOCol0 : Cfg::kOCol1);
+        uint32_t p_tmem = tmem + (t == 0 ? Cfg::kSCol0 : Cfg::kSCol1);
+        const int nk = ncols / Cfg::kMmaK;
+#pragma unroll
+        for (int kk = 0; kk < kChunkCols / Cfg::kMmaK; ++kk) {
+          // kMmaK kv rows per MMA: kMmaK x 128 B down the V panel; P advances 8 TMEM columns (32 bytes).
+          if (kk < nk) {
+            if constexpr (FP8) mma_ts_f8(d_tmem, p_tmem, mk64(b_lo, v_hi), idesc, (acc || kk > 0) ? 1u : 0u);
+            else mma_ts(d_tmem, p_tmem, mk64(b_lo, v_hi), idesc, (acc || kk > 0) ? 1u : 0u);
+            asm volatile("" : "+r"(p_tmem), "+r"(b_lo));
+            p_tmem += 8;
+            b_lo += (Cfg::kMmaK * 128) >> 4;
+          }
+        }
+      };
       mbar_wait(smem_u32(&bars->q_full), 0, 2);
       if constexpr (kGather) fence_proxy_async_smem();
       int ring = 0;
@@ -318,10 +430,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
         mbar_wait(smem_u32(&bars->kv_full[slot]), 0, 3);
         if constexpr (kGather) fence_proxy_async_smem();  // cp.async wrote through the generic proxy
         tc_fence_after();
-        issue_qk(0, slot, n_cur);
+        issue_qk(0, k_lo0, qk_idesc(n_cur));
         tc_commit(smem_u32(&bars->s_full[0]));
         if (ntiles > 1) {
-          issue_qk(1, slot, n_cur);
+          issue_qk(1, k_lo0, qk_idesc(n_cur));
           tc_commit(smem_u32(&bars->s_full[1]));
         }
         tc_commit(smem_u32(&bars->kv_empty[slot]));
@@ -340,28 +452,38 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
           ++ring;
           n_next = chunk_n(j + 1);
         }
+        // everything the MMAs need is computed before the waits
+        const uint32_t v_lo = v_lo0 + vslot * kSlotStep, k_lo = k_lo0 + kslot * kSlotStep;
+        const uint32_t idesc_next = qk_idesc(n_next);
         mbar_wait(smem_u32(&bars->kv_full[vslot]), vph, 4);
         if constexpr (kGather) fence_proxy_async_smem();
+        SVGB_TRACE(2, j, 0);
         mbar_wait(smem_u32(&bars->p_full[0]), j & 1, 5);
+        SVGB_TRACE(2, j, 1);
         tc_fence_after();
-        issue_pv(0, vslot, n_cur, j > 0);
+        issue_pv(0, v_lo, n_cur, j > 0);
         if (has_next) {
           mbar_wait(smem_u32(&bars->kv_full[kslot]), kph, 6);
           if constexpr (kGather) fence_proxy_async_smem();
           tc_fence_after();
-          issue_qk(0, kslot, n_next);
+          SVGB_TRACE(2, j, 2);
+          issue_qk(0, k_lo, idesc_next);
           tc_commit(smem_u32(&bars->s_full[0]));
+          SVGB_TRACE(2, j, 3);
         }
         if (ntiles > 1) {
           mbar_wait(smem_u32(&bars->p_full[1]), j & 1, 7);
+          SVGB_TRACE(2, j, 4);
           tc_fence_after();
-          issue_pv(1, vslot, n_cur, j > 0);
+          issue_pv(1, v_lo, n_cur, j > 0);
         }
         tc_commit(smem_u32(&bars->kv_empty[vslot]));
         if (has_next) {
           if (ntiles > 1) {
-            issue_qk(1, kslot, n_next);
+            SVGB_TRACE(2, j, 5);
+            issue_qk(1, k_lo, idesc_next);
             tc_commit(smem_u32(&bars->s_full[1]));
+            SVGB_TRACE(2, j, 6);
           }
           tc_commit(smem_u32(&bars->kv_empty[kslot]));
         }
@@ -415,8 +537,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
         const int ngroups = (ncols + 31) >> 5;
         if (!gather && j + 1 < nchunks) ch = __ldg(&chunks[j + 1]);
 
+        SVGB_TRACE(t, j, 0);
         mbar_wait(sbar, j & 1, 8 + t);
         tc_fence_after();
+        SVGB_TRACE(t, j, 1);
 
         // ---------------- single pass: the whole score row (<=128 columns) lives in registers.
         // Compiled twice: kPlain = full unmasked 128-column chunk (the common case, no guards at all) and
@@ -431,6 +555,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
           if (kPlain || ngroups > 2) tmem_ld32(s_addr + 64, r2);
           if (kPlain || ngroups > 3) tmem_ld32(s_addr + 96, r3);
           tc_wait_ld();
+          SVGB_TRACE(t, j, 2);
           if constexpr (!kPlain) {
             auto sanitize = [&](uint32_t(&rr)[32], int g) {
               const int left = valid - g * 32;
@@ -474,6 +599,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
               tmem_st32(o_addr + g * 32, o);
             }
           }
+          SVGB_TRACE(t, j, 3);
           l_run *= alpha;
           const float mc = (m_used == -INFINITY) ? 0.f : m_used * c - kPOff;
           const uint64_t c2 = pack_f32x2(c, c), nmc2 = pack_f32x2(-mc, -mc);
@@ -521,6 +647,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
           group_p(r1, 1);
           group_p(r2, 2);
           group_p(r3, 3);
+          SVGB_TRACE(t, j, 4);
           float s0, s1;
           unpack_f32x2(sum2, s0, s1);
           rs = s0 + s1;
@@ -529,8 +656,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
         else chunk_body(std::false_type{});
         l_run += rs;
         tc_wait_st();
+        SVGB_TRACE(t, j, 5);
         tc_fence_before();
         mbar_arrive(pbar);
+        SVGB_TRACE(t, j, 6);
       }
 
       // ---------------- epilogue: O / l -> 16-bit -> global (optionally scattered rows)
@@ -626,10 +755,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
 
 #pragma unroll 1
         for (int t = 0; t < ntiles; ++t) {
-          const uint32_t s_addr = lane_addr + (t == 0 ? Cfg::kSCol0 : Cfg::kSCol1);
+          // single-tile items ping-pong the two S buffers over the chunk stream (see the MMA issuer)
+          const int sb = ntiles == 1 ? (j & 1) : t;
+          const uint32_t s_addr = lane_addr + (sb == 0 ? Cfg::kSCol0 : Cfg::kSCol1);
           const uint32_t o_addr = lane_addr + (t == 0 ? Cfg::kOCol0 : Cfg::kOCol1);
           const int q = q_row0 + t * kTileRows + row;
-          mbar_wait(smem_u32(&bars->s_full[t]), j & 1, 8 + t);
+          mbar_wait(smem_u32(&bars->s_full[sb]), ntiles == 1 ? ((j >> 1) & 1) : (j & 1), 8 + t);
           tc_fence_after();
 
           float rs;
@@ -673,7 +804,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
               m_used[t] = m_new;
             }
             if (j > 0 && __any_sync(0xffffffffu, alpha != 1.f)) {
-              // correction of this thread's half of the O row (PV_t(j-1) is complete: S_t(j) commit covered it)
+              // correction of this thread's half of the O row.  Two-tile items: PV_t(j-1) is complete (the S_t(j)
+              // commit covered it).  Ping-pong items: PV(j-1) may still be accumulating -> wait for its commit.
+              if (ntiles == 1) {
+                mbar_wait(smem_u32(&bars->pv_done), (j - 1) & 1, 12);
+                tc_fence_after();
+              }
 #pragma unroll 1
               for (int g = 0; g < D / 64; ++g) {
                 uint32_t o[32];
@@ -740,7 +876,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
           l_run[t] += rs;
           tc_wait_st();
           tc_fence_before();
-          mbar_arrive(smem_u32(&bars->p_full[t]));
+          mbar_arrive(smem_u32(&bars->p_full[sb]));
         }
       }
 

@@ -153,21 +153,29 @@ kmeans_assign_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_cons
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {  // elect.sync: ptxas emits the tcgen05 stream without per-instruction election loops
       mbar_wait(smem_u32(&bars->x_full), 0, 32);
       const uint32_t idesc = make_idesc(128, 128, BF16, false, false);
+      // descriptors = constant high word + running low word (address field in units of 16 B), see attn_kernel.cuh
+      const uint64_t d0 = desc_kmajor_sw128(sX);
+      const uint32_t hi = static_cast<uint32_t>(d0 >> 32), x_lo0 = static_cast<uint32_t>(d0);
+      const uint32_t c_lo0 = static_cast<uint32_t>(desc_kmajor_sw128(sRing));
       for (int j = 0; j < nchunks; ++j) {
         const int slot = j % Cfg::kStages, buf = j & 1;
+        const uint32_t c_lo = c_lo0 + slot * (Cfg::kTileBytes >> 4);
         mbar_wait(smem_u32(&bars->c_full[slot]), (j / Cfg::kStages) & 1, 33);
         for (int t = 0; t < ntiles; ++t) {
           mbar_wait(smem_u32(&bars->s_empty[t][buf]), ((j >> 1) & 1) ^ 1, 34);
           tc_fence_after();
           const uint32_t d_tmem = tmem + t * 256 + buf * 128;
+          uint32_t a_lo = x_lo0 + t * (Cfg::kTileBytes >> 4), b_lo = c_lo;
 #pragma unroll
           for (int kk = 0; kk < D / 16; ++kk) {
-            const uint32_t off = (kk >> 2) * Cfg::kPanelBytes + (kk & 3) * 32;
-            mma_ss(d_tmem, desc_kmajor_sw128(sX + t * Cfg::kTileBytes + off),
-                   desc_kmajor_sw128(sRing + slot * Cfg::kTileBytes + off), idesc, kk > 0);
+            mma_ss(d_tmem, (static_cast<uint64_t>(hi) << 32) | a_lo, (static_cast<uint64_t>(hi) << 32) | b_lo, idesc, kk > 0);
+            asm volatile("" : "+r"(a_lo), "+r"(b_lo));
+            const uint32_t step = ((kk & 3) == 3) ? ((Cfg::kPanelBytes - 3 * 32) >> 4) : (32 >> 4);
+            a_lo += step;
+            b_lo += step;
           }
           tc_commit(smem_u32(&bars->s_full[t][buf]));
         }
