@@ -368,6 +368,37 @@ def run_ours(args):
         except Exception as e:  # noqa: BLE001
             fp8 = {"error": repr(e)[:200]}
 
+    # ---- pre-attention chain: fused transpose + QK-RMSNorm + RoPE, HBM-bound
+    prep = None
+    if rank == 0:
+        try:
+            qi, ki, vi = (torch.randn(1, S, Hl * D, device=dev).bfloat16() for _ in range(3))
+            gq, gk = (torch.randn(D, device=dev).bfloat16() for _ in range(2))
+            cos, sin = (torch.randn(S - CTX, D, device=dev) for _ in range(2))
+            outs = tuple(torch.empty(1, Hl, S, D, device=dev, dtype=torch.bfloat16) for _ in range(3))
+
+            def prep_call():
+                core.qkv_prep(qi, ki, vi, Hl, out=outs, norm=core.NORM_RMS_HEAD, gamma_q=gq, gamma_k=gk, eps=1e-6, rope=1,
+                              cos=cos, sin=sin, rope_lo=0, rope_n=S - CTX)
+            for _ in range(2):
+                prep_call()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(5):
+                prep_call()
+            b.record()
+            torch.cuda.synchronize()
+            msp = a.elapsed_time(b) / 5
+            nbytes = 6 * Hl * S * D * 2
+            hbm = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()).get("hbm_gbs") if (ROOT / "MEASURED_PEAKS.json").exists() else None
+            prep = {"workload": f"[1,S,{Hl}x{D}] q,k,v -> [1,{Hl},S,{D}]: transpose + per-head RMSNorm(q,k) + RoPE (text last)",
+                    "ms_per_call": msp, "algorithmic_bytes": nbytes, "gbs": nbytes / msp / 1e6,
+                    "hbm_peak_gbs": hbm, "frac": (nbytes / msp / 1e6 / hbm) if hbm else None}
+            del qi, ki, vi, outs
+        except Exception as e:  # noqa: BLE001
+            prep = {"error": repr(e)[:200]}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -404,7 +435,7 @@ def run_ours(args):
                          "seconds": dt_cpu},
         "e2e": {"value": flops_total / e2e_ms / 1e9, "unit": "TFLOP/s", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": bytes_in, "d2h_bytes_per_step": bytes_out},
-        "clocks": clocks, "gpu_launches": launches, "svg2": svg2, "fp8": fp8,
+        "clocks": clocks, "gpu_launches": launches, "svg2": svg2, "fp8": fp8, "prep": prep,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
