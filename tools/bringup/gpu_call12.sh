@@ -1,6 +1,6 @@
 #!/bin/bash
 # call 12: new prep / glue kernels (tests + probe), sample_mse merge change, bench for the e2e number
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 rm -f gpurun_out/prep.jsonl
 timeout 900 python -m pytest tests/test_prep_gpu.py tests/test_ops_api_gpu.py tests/test_svg2_ops_gpu.py -x -q -m gpu > gpurun_out/pytest_prep.log 2>&1

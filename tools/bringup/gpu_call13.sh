@@ -1,5 +1,5 @@
 #!/bin/bash
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 rm -f gpurun_out/prep.jsonl
 timeout 600 python -m pytest tests/test_prep_gpu.py -x -q -m gpu -k "glue or fused" > gpurun_out/pytest_prep2.log 2>&1

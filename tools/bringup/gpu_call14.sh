@@ -1,5 +1,5 @@
 #!/bin/bash
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 rm -f gpurun_out/prep.jsonl
 timeout 600 python -m pytest tests/test_prep_gpu.py tests/test_observability.py -x -q -m gpu > gpurun_out/pytest_prep3.log 2>&1

@@ -1,5 +1,5 @@
 #!/bin/bash
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 L=$PWD/sparse-videogen_b200/svgb200/_lib
 for i in 1 2; do
 SVGB200_LIB=$L/libsvgb200_base.so PERF_TAG=base timeout 300 python tools/ab_varblock.py | grep -E "aligned|QC1000|sample"

@@ -1,5 +1,5 @@
 #!/bin/bash
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 L=$PWD/sparse-videogen_b200/svgb200/_lib
 timeout 900 python -m pytest tests/test_attention_gpu.py tests/test_fp8_gpu.py tests/test_fullsize_gpu.py -x -q -m gpu > gpurun_out/pytest_lean.log 2>&1

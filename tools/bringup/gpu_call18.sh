@@ -1,5 +1,5 @@
 #!/bin/bash
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 L=$PWD/sparse-videogen_b200/svgb200/_lib
 SVGB200_LIB=$L/libsvgb200_trace.so timeout 200 python tools/attn_trace.py | tail -5
 for i in 1 2; do

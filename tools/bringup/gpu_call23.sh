@@ -1,5 +1,5 @@
 #!/bin/bash
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 L=$PWD/sparse-videogen_b200/svgb200/_lib
 timeout 900 python -m pytest tests/test_attention_gpu.py tests/test_fp8_gpu.py tests/test_fullsize_gpu.py tests/test_svg2_ops_gpu.py tests/test_ops_api_gpu.py -x -q -m gpu > gpurun_out/pytest_comb.log 2>&1

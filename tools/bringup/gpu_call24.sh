@@ -1,6 +1,6 @@
 #!/bin/bash
 # final round-1 evidence: full GPU suite, bench, stage timings, launch list, one ncu --set full of the band kernel
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 timeout 1200 python -m pytest tests -q -m gpu 2>&1 | tail -4
 timeout 900 python bench.py --steps 5 --warmup 3 > gpurun_out/bench_final.json 2> gpurun_out/bench_final.err; tail -3 gpurun_out/bench_final.err; cut -c1-700 gpurun_out/bench_final.json

@@ -1,5 +1,5 @@
 #!/bin/bash
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 L=$PWD/sparse-videogen_b200/svgb200/_lib
 timeout 600 python -m pytest tests/test_attention_gpu.py tests/test_fp8_gpu.py -x -q -m gpu 2>&1 | tail -2
 for v in base tree d; do
