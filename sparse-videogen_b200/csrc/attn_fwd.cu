@@ -1,5 +1,7 @@
 // Attention plans (device-built work lists), the attention launcher, density, and the tile
 // self-test.  See attn_kernel.cuh for the kernel itself.
+#include <stdlib.h>
+
 #include "../../include/svgb200.h"
 #include "attn_kernel.cuh"
 #include "host_common.h"
@@ -319,6 +321,17 @@ static int launch_attn(const CUtensorMap& qm, const CUtensorMap& km, const CUten
   if constexpr (DT != DT_E4M3) {
     if (args.gather) {
       auto kern = attn_fwd_kernel<D, DT, true>;
+      SVGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+      kern<<<grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(qm, km, vm, args);
+      SVGB_LAUNCH_OK();
+      return 0;
+    }
+  }
+  if constexpr (DT != DT_E4M3 && D == 128) {
+    // experimental sub-chunk pipeline (attn_kernel.cuh, kSub): opt-in until it is validated on the GPU
+    static const bool sub = [] { const char* e = getenv("SVGB_ATTN_SUB"); return e && e[0] == '1'; }();
+    if (sub && !args.softmax_shared) {
+      auto kern = attn_fwd_kernel<D, DT, false, true>;
       SVGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
       kern<<<grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(qm, km, vm, args);
       SVGB_LAUNCH_OK();

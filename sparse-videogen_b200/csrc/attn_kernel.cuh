@@ -61,6 +61,10 @@ struct AttnBars {
   uint64_t kv_full[8];
   uint64_t kv_empty[8];
   uint64_t pv_done;  // single-tile (ping-pong) items: completes once per PV
+  // sub-chunk pipeline (kSub): per (tile, 64-column half) S-ready / P-ready, per tile PV-complete
+  uint64_t sub_s[2][2];
+  uint64_t sub_p[2][2];
+  uint64_t sub_pv[2];
   uint32_t tmem_base;
   uint32_t pad_[3];
   float xch[2 * 2 * 128];  // row-max / row-sum exchange between the two halves of a row (double-buffered)
@@ -86,7 +90,7 @@ constexpr int kRegsSoftmax = 224;
 
 // kGather selects the producer: false = TMA boxes over contiguous key ranges (chunk list), true = cp.async
 // row gathers over a run list (separate instantiations keep each one's register footprint small).
-template <int D, int DT, bool kGather>
+template <int D, int DT, bool kGather, bool kSub = false>
 __global__ void __launch_bounds__(384, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant__ CUtensorMap kmap,
                 const __grid_constant__ CUtensorMap vmap, const AttnArgs args) {
@@ -94,6 +98,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
   constexpr bool BF16 = DT != DT_F16;  // output / 16-bit P format (fp8 inputs produce bf16 output)
   constexpr bool FP8 = DT == DT_E4M3;
   static_assert(!(FP8 && kGather), "row-gather producers are 16-bit only");
+  static_assert(!(kSub && (FP8 || kGather)), "the sub-chunk pipeline is built for 16-bit TMA plans");
   const int bh = blockIdx.y;
   const int n_items = args.item_count[bh * args.counts_stride];
   if (static_cast<int>(blockIdx.x) >= n_items) return;
@@ -136,6 +141,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
     mbar_init(smem_u32(&bars->q_full), n_prod);
     mbar_init(smem_u32(&bars->o_final), 1);
     mbar_init(smem_u32(&bars->pv_done), 1);
+    if constexpr (kSub) {
+      for (int t = 0; t < 2; ++t) {
+        mbar_init(smem_u32(&bars->sub_pv[t]), 1);
+        for (int h = 0; h < 2; ++h) {
+          mbar_init(smem_u32(&bars->sub_s[t][h]), 1);
+          mbar_init(smem_u32(&bars->sub_p[t][h]), 128);
+        }
+      }
+    }
     for (int t = 0; t < 2; ++t) {
       mbar_init(smem_u32(&bars->s_full[t]), 1);
       mbar_init(smem_u32(&bars->p_full[t]), per_tile_map ? 128 : 256);
@@ -421,6 +435,88 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
           }
         }
       };
+      if constexpr (kSub) {
+        // ---- sub-chunk pipeline (experimental, SVGB_ATTN_SUB=1): every 128-key chunk is two 64-key halves with
+        // their own S sub-buffer (S_t columns [64h, 64h+64), P over the first 32 of them).  QK_t,h(j+1) follows
+        // PV_t,h(j) immediately, i.e. while the softmax thread is still in the OTHER half of chunk j, so the
+        // softmax never waits for an MMA round trip.  sub_pv[t] completes once per PV group (the lazy O rescale
+        // of sub-step n waits for group n-1 on it).
+        auto half_cols = [](int n, int h) { return min(max(n - 64 * h, 0), 64); };
+        constexpr uint32_t kHalfRows = (64 * 128) >> 4;  // 64 key rows down a 128-byte-row panel, descriptor units
+        auto issue_qk_h = [&](int t, int h, uint32_t k_lo_slot, int nh) {
+          if (nh == 0) return;
+          const uint32_t idesc = make_idesc(128, nh, DT == DT_BF16, false, false);
+          const uint32_t d_tmem = tmem + (t == 0 ? Cfg::kSCol0 : Cfg::kSCol1) + 64 * h;
+          uint32_t a_lo = q_lo[t], b_lo = k_lo_slot + h * kHalfRows;
+#pragma unroll
+          for (int kk = 0; kk < Cfg::kRowBytes / 32; ++kk) {
+            mma_ss(d_tmem, mk64(a_lo, k_hi), mk64(b_lo, k_hi), idesc, kk > 0 ? 1u : 0u);
+            asm volatile("" : "+r"(a_lo), "+r"(b_lo));
+            const uint32_t step = ((kk & 3) == 3) ? ((Cfg::kPanelBytes - 3 * 32) >> 4) : (32 >> 4);
+            a_lo += step;
+            b_lo += step;
+          }
+        };
+        auto issue_pv_h = [&](int t, int h, uint32_t v_lo_slot, int nh, bool acc) {
+          const uint32_t idesc = make_idesc(128, D, DT == DT_BF16, false, true);
+          const uint32_t d_tmem = tmem + (t == 0 ? Cfg::kOCol0 : Cfg::kOCol1);
+          uint32_t p_tmem = tmem + (t == 0 ? Cfg::kSCol0 : Cfg::kSCol1) + 64 * h;
+          uint32_t b_lo = v_lo_slot + h * kHalfRows;
+          const int nk = nh / Cfg::kMmaK;
+#pragma unroll
+          for (int kk = 0; kk < 64 / Cfg::kMmaK; ++kk) {
+            if (kk < nk) {
+              mma_ts(d_tmem, p_tmem, mk64(b_lo, v_hi), idesc, (acc || kk > 0) ? 1u : 0u);
+              asm volatile("" : "+r"(p_tmem), "+r"(b_lo));
+              p_tmem += 8;
+              b_lo += (Cfg::kMmaK * 128) >> 4;
+            }
+          }
+        };
+        mbar_wait(smem_u32(&bars->q_full), 0, 2);
+        int n_cur = chunk_n(0);
+        mbar_wait(smem_u32(&bars->kv_full[0]), 0, 3);
+        tc_fence_after();
+        for (int h = 0; h < 2; ++h)
+          for (int t = 0; t < 2; ++t) {
+            issue_qk_h(t, h, k_lo0, half_cols(n_cur, h));
+            tc_commit(smem_u32(&bars->sub_s[t][h]));
+          }
+        tc_commit(smem_u32(&bars->kv_empty[0]));
+        int ring = 1;
+        for (int j = 0; j < nchunks; ++j) {
+          const bool has_next = (j + 1 < nchunks);
+          const int vslot = ring % kStages;
+          const uint32_t vph = (ring / kStages) & 1;
+          ++ring;
+          int kslot = 0, n_next = 0;
+          uint32_t kph = 0;
+          if (has_next) {
+            kslot = ring % kStages;
+            kph = (ring / kStages) & 1;
+            ++ring;
+            n_next = chunk_n(j + 1);
+          }
+          const uint32_t v_lo = v_lo0 + vslot * kSlotStep, k_lo = k_lo0 + kslot * kSlotStep;
+          mbar_wait(smem_u32(&bars->kv_full[vslot]), vph, 4);
+          if (has_next) mbar_wait(smem_u32(&bars->kv_full[kslot]), kph, 6);
+          for (int h = 0; h < 2; ++h)
+            for (int t = 0; t < 2; ++t) {
+              mbar_wait(smem_u32(&bars->sub_p[t][h]), j & 1, 5 + t);
+              tc_fence_after();
+              issue_pv_h(t, h, v_lo, half_cols(n_cur, h), j > 0 || h > 0);
+              tc_commit(smem_u32(&bars->sub_pv[t]));
+              if (has_next) {
+                issue_qk_h(t, h, k_lo, half_cols(n_next, h));
+                tc_commit(smem_u32(&bars->sub_s[t][h]));
+              }
+            }
+          tc_commit(smem_u32(&bars->kv_empty[vslot]));
+          if (has_next) tc_commit(smem_u32(&bars->kv_empty[kslot]));
+          n_cur = n_next;
+        }
+        tc_commit(smem_u32(&bars->o_final));
+      } else {
       mbar_wait(smem_u32(&bars->q_full), 0, 2);
       if constexpr (kGather) fence_proxy_async_smem();
       int ring = 0;
@@ -490,6 +586,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
         n_cur = n_next;
       }
       tc_commit(smem_u32(&bars->o_final));
+      }
     }
   } else if (warp < 4) {
     setmaxnreg_dec<kRegsLight>();
@@ -529,6 +626,112 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
       MaskRow mrow;
       mrow.init(mode, qm, m0, m1, m2);
 
+      if constexpr (kSub) {
+      // ---- sub-chunk pipeline: two 64-column online-softmax steps per chunk (see the MMA issuer)
+      int nsub = 0;  // PV groups issued into O_t so far == sub-steps finished
+      for (int j = 0; j < nchunks; ++j) {
+        const int kv0 = ch.x;
+        const int valid = chunk_valid(ch.y);
+        const bool elem = (ch.y & kChunkElem) != 0;
+        const int ncols = (valid + Cfg::kMmaK - 1) & ~(Cfg::kMmaK - 1);
+        if (j + 1 < nchunks) ch = __ldg(&chunks[j + 1]);
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h, ++nsub) {
+          const int nh = min(max(ncols - 64 * h, 0), 64);  // MMA columns of this half
+          const int vh = min(max(valid - 64 * h, 0), 64);  // valid key columns of this half
+          const uint32_t sh_addr = s_addr + 64 * h;
+          mbar_wait(smem_u32(&bars->sub_s[t][h]), j & 1, 8 + t);
+          tc_fence_after();
+          if (nh > 0) {
+            float rs;
+            auto half_body = [&](auto plain_tag) {
+              constexpr bool kPlain = decltype(plain_tag)::value;
+              uint32_t r0[32], r1[32];
+              tmem_ld32(sh_addr, r0);
+              if (kPlain || nh > 32) tmem_ld32(sh_addr + 32, r1);
+              tc_wait_ld();
+              if constexpr (!kPlain) {
+                auto sanitize = [&](uint32_t(&rr)[32], int gl) {
+                  const int left = vh - gl * 32;
+                  if (gl * 32 >= nh || !(elem || left < 32)) return;  // warp-uniform
+                  uint32_t bits = left >= 32 ? 0xffffffffu : (left > 0 ? (1u << left) - 1u : 0u);
+                  if (elem && left > 0) bits &= mrow.bits32(kv0 + 64 * h + gl * 32);
+#pragma unroll
+                  for (int i = 0; i < 32; ++i) rr[i] = (bits >> i) & 1u ? rr[i] : 0xff800000u;  // -inf
+                };
+                sanitize(r0, 0);
+                sanitize(r1, 1);
+              }
+              float mx = -INFINITY;
+#pragma unroll
+              for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r0[i]));
+              if (kPlain || nh > 32) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r1[i]));
+              }
+              const float m_new = fmaxf(m_used, mx);
+              float alpha = 1.f;
+              if ((m_new - m_used) * c > kTau) {
+                alpha = ex2_approx((m_used - m_new) * c);
+                m_used = m_new;
+              }
+              if (nsub > 0 && __any_sync(0xffffffffu, alpha != 1.f)) {
+                // every PV group issued so far must have landed in O_t before it is rescaled
+                mbar_wait(smem_u32(&bars->sub_pv[t]), (nsub - 1) & 1, 12);
+                tc_fence_after();
+#pragma unroll 1
+                for (int g = 0; g < D / 32; ++g) {
+                  uint32_t o[32];
+                  tmem_ld32(o_addr + g * 32, o);
+                  tc_wait_ld();
+#pragma unroll
+                  for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                  tmem_st32(o_addr + g * 32, o);
+                }
+              }
+              l_run *= alpha;
+              const float mc = (m_used == -INFINITY) ? 0.f : m_used * c - kPOff;
+              const uint64_t c2 = pack_f32x2(c, c), nmc2 = pack_f32x2(-mc, -mc);
+              uint64_t sum2 = pack_f32x2(0.f, 0.f);
+              auto group_p = [&](const uint32_t(&rr)[32], int gl) {
+                if constexpr (!kPlain) {
+                  if (gl * 32 >= nh) return;
+                }
+                uint32_t pk[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                  const uint64_t x2 =
+                      ffma2(pack_f32x2(__uint_as_float(rr[2 * i]), __uint_as_float(rr[2 * i + 1])), c2, nmc2);
+                  float p0, p1;
+                  if ((i & 3) == 3) {
+                    ex2_poly2(x2, p0, p1);
+                  } else {
+                    float x0, x1;
+                    unpack_f32x2(x2, x0, x1);
+                    p0 = ex2_approx(x0);
+                    p1 = ex2_approx(x1);
+                  }
+                  sum2 = fadd2(sum2, pack_f32x2(p0, p1));
+                  pk[i] = pack2<BF16>(p0, p1);
+                }
+                tmem_st16(sh_addr + gl * 16, pk);
+              };
+              group_p(r0, 0);
+              group_p(r1, 1);
+              float s0, s1;
+              unpack_f32x2(sum2, s0, s1);
+              rs = s0 + s1;
+            };
+            if (!elem && vh == 64) half_body(std::true_type{});
+            else half_body(std::false_type{});
+            l_run += rs;
+            tc_wait_st();
+          }
+          tc_fence_before();
+          mbar_arrive(smem_u32(&bars->sub_p[t][h]));
+        }
+      }
+      } else
       for (int j = 0; j < nchunks; ++j) {
         const int kv0 = ch.x;
         const int valid = gather ? min(kChunkCols, total_kv - j * kChunkCols) : chunk_valid(ch.y);
