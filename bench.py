@@ -130,23 +130,42 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------------
 # reference arm / cpu_baseline: naive masked attention on the host cores, bounded sample
 # ---------------------------------------------------------------------------------------------------
-def cpu_naive_sample(rows=1024, seconds_hint=None):
-    """One head, `rows` query rows spread over the sequence, full S keys, HY band mask, fp32.
-    Returns (tflops, seconds, sample description).  Same arithmetic as ref_torch_attn_impl."""
+def usable_cores():
+    """Host threads this process may really use: cpu_count capped by the affinity mask and the cgroup CPU quota
+    (a container can report 128 CPUs and be allowed 16; oversubscribing makes the CPU arm look worse than it is)."""
+    n = os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except (AttributeError, OSError):
+        pass
+    try:
+        quota, period = (Path("/sys/fs/cgroup/cpu.max").read_text().split() + ["100000"])[:2]
+        if quota != "max":
+            n = min(n, max(1, int(int(quota) / int(period))))
+    except (OSError, ValueError):
+        pass
+    return max(1, n)
+
+
+def cpu_naive_sample(rows=1024, seconds=10.0):
+    """One head, up to `rows` query rows spread over the sequence (256 at a time, until `seconds` of work are
+    done), full S keys, HY band mask, fp32.  Returns (tflops, seconds, sample description, threads).  Same
+    arithmetic as ref_torch_attn_impl (svg/kernels/test/test_sparse_attn.py:109-157)."""
     from oracle.attention import hy_mask_mod
 
-    cores = os.cpu_count() or 1
+    cores = usable_cores()
     torch.set_num_threads(cores)
     W, mul = band_width()
     g = torch.Generator().manual_seed(0)
     k = torch.randn(S, D, generator=g)
     v = torch.randn(S, D, generator=g)
     qrows = torch.linspace(0, S - 1, rows).long()
+    qrows = qrows[torch.randperm(rows, generator=g)]  # any prefix of the sample covers the whole sequence
     q = torch.randn(rows, D, generator=g)
     mod = hy_mask_mod(CTX, PROMPT_LEN, F, P, mul)
     kv_idx = torch.arange(S).view(1, S)
     t0 = time.perf_counter()
-    pairs = 0
+    pairs, done = 0, 0
     for r0 in range(0, rows, 256):
         qi = qrows[r0:r0 + 256].view(-1, 1)
         s = (q[r0:r0 + 256] @ k.T) / math.sqrt(D)
@@ -155,11 +174,15 @@ def cpu_naive_sample(rows=1024, seconds_hint=None):
         w = torch.softmax(s, dim=-1)
         _ = w @ v
         pairs += int(m.sum().item())
+        done += qi.numel()
+        if time.perf_counter() - t0 >= seconds:
+            break
     dt = time.perf_counter() - t0
     # the naive formulation computes every (q, kv) pair and masks afterwards; credit only the
     # algorithmic (allowed) pairs so the unit matches the GPU arm
     flops = 4.0 * D * pairs
-    return flops / dt / 1e12, dt, f"1 head, {rows} query rows evenly spaced over S={S}, all keys, HY band W={W}", cores
+    return (flops / dt / 1e12, dt,
+            f"1 head, {done} query rows spread over S={S}, all keys, HY band W={W}, {cores} threads", cores)
 
 
 def run_reference(args):
@@ -168,7 +191,7 @@ def run_reference(args):
         return
     vals, secs = [], []
     for i in range(args.warmup + args.steps):
-        tf, dt, sample, cores = cpu_naive_sample(rows=512)
+        tf, dt, sample, cores = cpu_naive_sample(rows=4096, seconds=10.0)
         if i >= args.warmup:
             vals.append(tf)
             secs.append(dt)
@@ -181,9 +204,11 @@ def run_reference(args):
         "unit": "TFLOP/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": sum(secs) / len(secs) * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "HunyuanVideo-720p SVG1 band mask rho=0.30 (S=119056,H=24,D=128)",
-                   "note": "naive torch attention on host cores, bounded sample; ms/call extrapolated",
-                   "extrapolated_ms_per_call": ms_call},
+        "config": {"workload": "HunyuanVideo-720p SVG1 sparse attention core (sample_mse + placement + band attention "
+                               "+ inverse placement), rho=0.30", "S": S, "heads": H_TOTAL, "head_dim": D,
+                   "band_W": W, "density": pairs / S / S,
+                   "note": "the reference's naive torch attention on the host cores, bounded sample per step; "
+                           "ms per call extrapolated", "extrapolated_ms_per_call": ms_call},
         "cpu_baseline": {"value": value, "unit": "TFLOP/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -413,7 +438,7 @@ def run_ours(args):
             traffic = json.loads(tj.read_text()).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
-    tf_cpu, dt_cpu, sample, cores = cpu_naive_sample(rows=1024)
+    tf_cpu, dt_cpu, sample, cores = cpu_naive_sample(rows=4096, seconds=12.0)
     value = flops_total / ms_step / 1e9
     bytes_in = 3 * Hl * S * D * 2
     bytes_out = Hl * S * D * 2
