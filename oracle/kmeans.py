@@ -13,7 +13,6 @@ reference -> restated from source, parity UNPINNED by reference outputs.
 """
 from __future__ import annotations
 
-import numpy as np
 import torch
 
 

@@ -6,7 +6,6 @@ attention core consumes.
 """
 from __future__ import annotations
 
-from typing import Optional
 
 import torch
 
