@@ -329,11 +329,13 @@ static int launch_attn(const CUtensorMap& qm, const CUtensorMap& km, const CUten
   }
   if constexpr (DT != DT_E4M3 && D == 128) {
     // experimental sub-chunk pipeline (attn_kernel.cuh, kSub): opt-in until it is validated on the GPU
-    static const bool sub = [] { const char* e = getenv("SVGB_ATTN_SUB"); return e && e[0] == '1'; }();
+    static const int sub = [] { const char* e = getenv("SVGB_ATTN_SUB"); return (e && (e[0] == '1' || e[0] == '2')) ? e[0] - '0' : 0; }();
     if (sub && !args.softmax_shared) {
       auto kern = attn_fwd_kernel<D, DT, false, true>;
       SVGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-      kern<<<grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(qm, km, vm, args);
+      AttnArgs sub_args = args;
+      sub_args.sub_mode = sub;
+      kern<<<grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(qm, km, vm, sub_args);
       SVGB_LAUNCH_OK();
       return 0;
     }
@@ -530,6 +532,7 @@ static int attn_fwd_entry(const void* q, const void* k, const void* v, const flo
   a.out_f32 = 0;
   // variable-block plans over small key clusters are made of narrow chunks: latency-bound steps
   a.softmax_shared = (plan->kind == 1 && plan->m1 > 0 && plan->m1 < 256) ? 1 : 0;
+  a.sub_mode = 0;
   a.q_scale = q_scale;
   a.k_scale = k_scale;
   a.v_scale = v_scale;
