@@ -184,7 +184,10 @@ int svgb_dynamic_map(const void* qc, const void* kc, const int32_t* k_sizes, int
                      int D, int dtype, float top_p, int preserve, uint8_t* map, void* stream);
 /* sample_mse (hyvideo/attention.py:375-399): MSE between full attention and attention under the two
  * profiling masks (0 spatial, 1 temporal) on `n_rows` sampled query rows -> float [2, BH].
- * layout: 0 = HY (text last, band 1.5*P), 1 = WAN (first-frame sink, band 2*P), 2 = COG. */
+ * layout: 0 = HY (text last, band 1.5*P; hyvideo/utils.py:47-93), 1 = WAN (first-frame sink, band 2*P;
+ * wan/utils.py:63-110), 2 = COG (text first, band 1.5*P; cog/utils.py:61-88 -- its temporal mask leaves text rows
+ * empty: a sampled text row contributes 0 output here where the reference's softmax yields NaN; the Python mirror
+ * CogSVG1Core.sample_mse restores the NaN so argmin picks the same head type). */
 int svgb_sample_mse_bytes(int BH, int S, int D, int n_rows, size_t* bytes);
 int svgb_sample_mse(const void* q, const void* k, const void* v, const int32_t* rows, int n_rows,
                     int BH, int S, int D, int dtype, int layout, int ctx, int F, int P, float* mse,

@@ -214,6 +214,35 @@ def profiling_mask_rows(mask_name, rows, layout, context_length, num_frame, fram
     return out
 
 
+def profiling_mask_rows_cog(mask_name, rows, context_length, num_frame, frame_size):
+    """Rows of the CogVideoX profiling masks (text FIRST), svg/models/cog/utils.py:61-88, analytically.
+
+    spatial : text rows / columns all-ones (:66-67); the 128-token block band |bi-bj| < (1.5*P)//128 is painted in
+              ABSOLUTE coordinates from row / column 0 for blocks 0..ceil(F*P/128)-1 (:68-74, not offset by the text);
+    temporal: the same band picture pushed through reshape(P,F,P,F).permute(1,0,3,2) on the video x video part only
+              (:76-86); text rows and text columns stay ZERO (a sampled text row is fully masked)."""
+    F_, P_, ctx = num_frame, frame_size, context_length
+    V = F_ * P_
+    S = ctx + V
+    thres = (frame_size * 1.5) // 128
+    lim = math.ceil(V / 128) * 128
+    kv = torch.arange(S)
+    out = torch.zeros(len(rows), S, dtype=torch.bool)
+    for n, r in enumerate([int(x) for x in rows]):
+        if mask_name == "spatial":
+            band = ((r // 128 - kv // 128).abs() < thres) & (kv < lim) & (r < lim)
+            out[n] = band | (kv < ctx) | (r < ctx)
+        else:
+            if r < ctx:
+                continue
+            qv = r - ctx
+            kvv = kv[ctx:] - ctx
+            qi = (qv % P_) * F_ + qv // P_
+            ki = (kvv % P_) * F_ + kvv // P_
+            out[n, ctx:] = (qi // 128 - ki // 128).abs() < thres
+    return out
+
+
 def sample_mse(q, k, v, sampled_rows, masks_rows):
     """hyvideo/attention.py:375-399 in fp32.  q,k,v [cfg,H,S,D]; masks_rows: list of bool
     [n_rows, S] (rows of the profiling masks at sampled_rows) -> fp32 [n_masks, cfg, H]."""
@@ -259,11 +288,14 @@ def get_factor(num_tokens_per_frame):
     raise ValueError
 
 
-def ref_gen_temporal_mask_wan(num_frames, num_tokens_per_frame, multiplier):
-    """wan/utils.py:130-185 / ops/attention_ops_wan.py:96-129 (adds the first-frame region)."""
+def ref_gen_temporal_mask_wan(num_frames, num_tokens_per_frame, multiplier, first_frame=True):
+    """first_frame=True: svg/models/wan/utils.py:130-185 (band + every block whose centre lies in the first frame,
+    :168); first_frame=False: svg/kernels/ops/attention_ops_wan.py:48-129 (band only)."""
     bs = get_factor(num_tokens_per_frame)
     n = num_frames * num_tokens_per_frame // bs
     i = np.arange(n)[:, None] * bs + bs // 2
     j = np.arange(n)[None, :] * bs + bs // 2
-    keep = (np.abs(i - j) < multiplier * num_tokens_per_frame) | (j <= num_tokens_per_frame)
+    keep = np.abs(i - j) < multiplier * num_tokens_per_frame
+    if first_frame:
+        keep = keep | (j <= num_tokens_per_frame)
     return np.where(keep, np.arange(n)[None, :], -1), (bs, bs)

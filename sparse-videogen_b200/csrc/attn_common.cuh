@@ -42,6 +42,13 @@ enum MaskMode : int {
   MASK_PROF_HY_T = 5,
   MASK_PROF_WAN_S = 6,
   MASK_PROF_WAN_T = 7,
+  // CogVideoX (text FIRST) profiling masks, svg/models/cog/utils.py:61-88.  m2 = thres | ctx << 12.
+  //   spatial : text rows / columns all-ones; the 128-token block band is painted in ABSOLUTE sequence
+  //             coordinates (blocks 0 .. ceil(F*P/128)-1 from row / column 0, cog/utils.py:68-74)
+  //   temporal: band in token-major order on the video x video part only; text rows and columns stay zero
+  //             (cog/utils.py:76-86) -- a sampled text row has no allowed key at all
+  MASK_PROF_COG_S = 8,
+  MASK_PROF_COG_T = 9,
 };
 
 __host__ __device__ inline bool mask_allowed(int mode, int q, int kv, int m0, int m1, int m2) {
@@ -59,6 +66,22 @@ __host__ __device__ inline bool mask_allowed(int mode, int q, int kv, int m0, in
       return (kv < m0) | (d <= m2);
     case MASK_COG:
       return (kv < m0) | (q < m1) | (d < m2);
+    case MASK_PROF_COG_S: {
+      const int thres = m2 & 0xfff, ctx = m2 >> 12;
+      const int lim = ((m0 * m1 + 127) / 128) * 128;
+      int bd = q / 128 - kv / 128;
+      bd = bd < 0 ? -bd : bd;
+      return (q < ctx) | (kv < ctx) | ((q < lim) & (kv < lim) & (bd < thres));
+    }
+    case MASK_PROF_COG_T: {
+      const int thres = m2 & 0xfff, ctx = m2 >> 12;
+      if (q < ctx || kv < ctx) return false;
+      const int F = m0, P = m1;
+      const int qv = q - ctx, kvv = kv - ctx;
+      int bd = ((qv % P) * F + qv / P) / 128 - ((kvv % P) * F + kvv / P) / 128;
+      bd = bd < 0 ? -bd : bd;
+      return bd < thres;
+    }
     case MASK_PROF_HY_S:
     case MASK_PROF_HY_T:
     case MASK_PROF_WAN_S:
@@ -88,7 +111,7 @@ struct MaskRow {
   __device__ __forceinline__ void init(int mode_, int q_, int m0_, int m1_, int m2_) {
     mode = mode_; q = q_; m0 = m0_; m1 = m1_; m2 = m2_;
     qi_blk = 0; q_text = false;
-    if (mode >= MASK_PROF_HY_S) {
+    if (mode >= MASK_PROF_HY_S && mode <= MASK_PROF_WAN_T) {
       const int F = m0, P = m1, V = F * P;
       const bool temporal = (mode == MASK_PROF_HY_T) | (mode == MASK_PROF_WAN_T);
       q_text = q >= V;
@@ -99,7 +122,7 @@ struct MaskRow {
   // bit i set <=> (q, kv0 + i) allowed
   __device__ __forceinline__ uint32_t bits32(int kv0) const {
     uint32_t out = 0;
-    if (mode >= MASK_PROF_HY_S) {
+    if (mode >= MASK_PROF_HY_S && mode <= MASK_PROF_WAN_T) {
       const int F = m0, P = m1, V = F * P;
       const bool hy = mode <= MASK_PROF_HY_T;
       const bool temporal = (mode == MASK_PROF_HY_T) | (mode == MASK_PROF_WAN_T);

@@ -163,9 +163,10 @@ int svgb_sample_mse(const void* q, const void* k, const void* v, const int32_t* 
   size_t need = 0;
   if (svgb_sample_mse_bytes(BH, S, D, n_rows, &need)) return -1;
   SVGB_REQUIRE(ws_bytes >= need, "workspace too small: %zu < %zu", ws_bytes, need);
-  SVGB_REQUIRE(layout == 0 || layout == 1, "layout %d unsupported (0 = HY text-last, 1 = WAN)", layout);
+  SVGB_REQUIRE(layout >= 0 && layout <= 2, "layout %d unsupported (0 = HY text-last, 1 = WAN, 2 = COG text-first)", layout);
   SVGB_REQUIRE(S == ctx + F * P, "seq_len %d != ctx %d + F %d * P %d", S, ctx, F, P);
-  SVGB_REQUIRE(layout == 0 || ctx == 0, "WAN layout has no text tokens");
+  SVGB_REQUIRE(layout != 1 || ctx == 0, "WAN layout has no text tokens");
+  SVGB_REQUIRE(layout != 2 || ctx < (1 << 19), "COG layout: context length %d too large", ctx);
   const SmseLayout L = smse_layout(BH, S, D);
   char* w = static_cast<char*>(ws);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -180,8 +181,11 @@ int svgb_sample_mse(const void* q, const void* k, const void* v, const int32_t* 
                                       reinterpret_cast<int2*>(w + L.chunks_plain),
                                       reinterpret_cast<int2*>(w + L.chunks_elem));
   SVGB_LAUNCH_OK();
-  // reference thresholds: block_thres // block_size with block_thres = 1.5*P (HY) or 2*P (WAN)
-  const int thres = layout == 0 ? static_cast<int>((1.5 * P) / 128.0) : (2 * P) / 128;
+  // reference thresholds: block_thres // block_size with block_thres = 1.5*P (HY, COG) or 2*P (WAN)
+  const int thres = layout == 1 ? (2 * P) / 128 : static_cast<int>((1.5 * P) / 128.0);
+  SVGB_REQUIRE(thres < (1 << 12), "profiling band threshold %d too large", thres);
+  static const int kModes[3][2] = {{MASK_PROF_HY_S, MASK_PROF_HY_T}, {MASK_PROF_WAN_S, MASK_PROF_WAN_T},
+                                   {MASK_PROF_COG_S, MASK_PROF_COG_T}};
   for (int var = 0; var < 3; ++var) {
     AttnArgs a;
     a.items = reinterpret_cast<const int4*>(w + L.items);
@@ -196,11 +200,10 @@ int svgb_sample_mse(const void* q, const void* k, const void* v, const int32_t* 
     a.lse = reinterpret_cast<float*>(w + L.lse_part) + static_cast<size_t>(var) * BH * rows_per_head;
     a.scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(D));
     a.S = rows_per_head;
-    a.mask_mode = var == 0 ? MASK_NONE : (layout == 0 ? (var == 1 ? MASK_PROF_HY_S : MASK_PROF_HY_T)
-                                                      : (var == 1 ? MASK_PROF_WAN_S : MASK_PROF_WAN_T));
+    a.mask_mode = var == 0 ? MASK_NONE : kModes[layout][var - 1];
     a.m0 = F;
     a.m1 = P;
-    a.m2 = thres;
+    a.m2 = layout == 2 ? (thres | (ctx << 12)) : thres;
     a.q_index = reinterpret_cast<const int*>(w + L.qidx);
     a.out_f32 = 1;
     a.softmax_shared = 0;

@@ -11,6 +11,16 @@ from ..placement import wan_hidden_states_placement, wan_sparse_head_placement  
 from .common import BandMask, KMeansState, SAPCore, SVG1Core, sparse_flex_attention, sparsity_to_width  # noqa: F401
 
 
+def gen_temporal_mask(num_frames: int, num_tokens_per_frame: int, multiplier: float, device=None):
+    """svg/models/wan/utils.py:130-185: BSR temporal mask = diagonal band + first-frame region."""
+    from ..ops.attention_ops_wan import gen_temporal_mask as _g
+
+    return _g(num_frames, num_tokens_per_frame, multiplier, device, first_frame=True)
+
+
+from ..ops.attention_ops_wan import flashinfer_sparse_attn_forward  # noqa: E402,F401  (wan/utils.py:188-238)
+
+
 def band_params(num_frames, token_per_frame, mul):
     """generate_temporal_head_mask_mod (wan/utils.py:25-41): kv < P | |q-kv| <= ceil(mul*P/128)*128."""
     return core.MASK_WAN, token_per_frame, 0, ceil(mul * token_per_frame / 128) * 128

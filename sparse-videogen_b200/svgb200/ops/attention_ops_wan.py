@@ -22,13 +22,19 @@ def get_factor(num_frames: int, num_tokens_per_frame: int) -> int:
     raise ValueError(f"No factor found for {num_frames} * {num_tokens_per_frame}")
 
 
-def gen_temporal_mask(num_frames: int, num_tokens_per_frame: int, multiplier: float, device=None):
-    """wan/utils.py:130-185 / attention_ops_wan.py:48-93: diagonal band + first-frame region."""
+def gen_temporal_mask(num_frames: int, num_tokens_per_frame: int, multiplier: float, device=None,
+                      first_frame: bool = False):
+    """svg/kernels/ops/attention_ops_wan.py:48-93: the diagonal band only (block centres closer than mul*P).
+    first_frame=True is the variant of svg/models/wan/utils.py:130-185, which also keeps every block whose centre lies
+    in the first frame (`elif col_token_idx <= num_tokens_per_frame`, wan/utils.py:168) -- exported under the
+    reference's name as svgb200.models.wan.gen_temporal_mask."""
     bs = get_factor(num_frames, num_tokens_per_frame)
     assert (num_tokens_per_frame * num_frames) % bs == 0
     n = num_frames * num_tokens_per_frame // bs
     c = np.arange(n) * bs + bs // 2
-    keep = (np.abs(c[:, None] - c[None, :]) < multiplier * num_tokens_per_frame) | (c[None, :] <= num_tokens_per_frame)
+    keep = np.abs(c[:, None] - c[None, :]) < multiplier * num_tokens_per_frame
+    if first_frame:
+        keep = keep | (c[None, :] <= num_tokens_per_frame)
     return _bsr_from_keep(keep, (bs, bs), device)
 
 

@@ -1,0 +1,32 @@
+"""Seeded input generators shared by the golden-vector scripts and the tests that consume the vectors, so that large
+random inputs are stored as (seed, checksum) instead of raw tensors.  torch's CPU generator is bit-reproducible for a
+given torch build (the GPU box runs the same image); every consumer checks the stored checksum first."""
+import torch
+
+
+def smse_inputs(seed, cfg, H, S, D):
+    """q, k, v bf16 [cfg,H,S,D]; head 0 gets strongly local structure so that the two profiling masks differ."""
+    g = torch.Generator().manual_seed(int(seed))
+    q, k, v = (torch.randn(cfg, H, S, D, generator=g).bfloat16() for _ in range(3))
+    k[:, 0] = k[:, 0] * 0.2 + q[:, 0]
+    return q, k, v
+
+
+def checksum(*ts):
+    return float(sum(t.double().sum().item() + (t.double() ** 2).sum().item() for t in ts))
+
+
+def kmeans_inputs(seed, B, N, D, K, clustered=True):
+    """x bf16 [B,N,D] (mixture of K/4 well-separated blobs + noise when `clustered`), init centroids = rows of x."""
+    g = torch.Generator().manual_seed(int(seed))
+    if clustered:
+        nb = max(2, K // 4)
+        centers = torch.randn(B, nb, D, generator=g) * 2.0
+        which = torch.randint(0, nb, (B, N), generator=g)
+        x = torch.gather(centers, 1, which[..., None].expand(-1, -1, D)) + torch.randn(B, N, D, generator=g)
+    else:
+        x = torch.randn(B, N, D, generator=g)
+    x = x.bfloat16()
+    idx = torch.randint(0, N, (B, K), generator=g)
+    init = torch.gather(x, 1, idx[..., None].expand(-1, -1, D)).contiguous()
+    return x, init

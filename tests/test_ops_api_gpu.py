@@ -34,17 +34,24 @@ def test_sparse_attn_forward_text_first(cuda, pattern, mul, H, D):
     torch.testing.assert_close(o, ref, **TOL[torch.float16])
 
 
+@pytest.mark.parametrize("first_frame", [False, True])
 @pytest.mark.parametrize("mul", [1.3, 2.2])
-def test_wan_sparse_attn_forward(cuda, mul):
+def test_wan_sparse_attn_forward(cuda, mul, first_frame):
+    """first_frame=False: svg/kernels/ops/attention_ops_wan.gen_temporal_mask (band only);
+    True: svg/models/wan/utils.gen_temporal_mask (band + first-frame region)."""
     from oracle import attention as oa
-    from svgb200.ops import WanFAMetadata, flashinfer_sparse_attn_forward, gen_temporal_mask, wan_sparse_attn_forward
+    from svgb200.models import wan as wan_m
+    from svgb200.ops import WanFAMetadata, flashinfer_sparse_attn_forward, wan_sparse_attn_forward
+    from svgb200.ops import gen_temporal_mask as ops_gen
+
+    gen_temporal_mask = wan_m.gen_temporal_mask if first_frame else ops_gen
 
     F, P, H, D = 5, 240, 2, 128
     S = F * P
     g = torch.Generator().manual_seed(1)
     q, k, v = (torch.randn(S, H, D, generator=g).to(torch.bfloat16) for _ in range(3))
     md = gen_temporal_mask(F, P, mul, device=cuda)
-    ref_bm, bs = oa.ref_gen_temporal_mask_wan(F, P, mul)
+    ref_bm, bs = oa.ref_gen_temporal_mask_wan(F, P, mul, first_frame=first_frame)
     assert tuple(md[2]) == tuple(bs)
     o = wan_sparse_attn_forward(q.to(cuda), k.to(cuda), v.to(cuda), WanFAMetadata(F, P, md)).float().cpu()
     ref = oa.ref_torch_attn_impl(q, k, v, oa.gen_mask_block2element(ref_bm, bs, 0))
