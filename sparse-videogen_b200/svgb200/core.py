@@ -78,10 +78,15 @@ class AttnPlan:
 
 
 def plan_varblock(block_map: torch.Tensor, row_sz: torch.Tensor, col_sz: torch.Tensor, S: int,
-                  ws: Optional[torch.Tensor] = None, gather: bool = False) -> AttnPlan:
+                  ws: Optional[torch.Tensor] = None, gather: bool = False, shared_scratch: bool = False) -> AttnPlan:
     """block_map [BH,QC,KC] bool/uint8, row_sz [BH,QC], col_sz [BH,KC] (any int dtype) on GPU.
     gather=True lowers the map for the row-gather kernel path (exactly-full chunks, optional fused
-    permutation through attn_fwd(..., q_rows=, kv_rows=))."""
+    permutation through attn_fwd(..., q_rows=, kv_rows=)).
+
+    Workspace ownership: by default every plan gets its OWN device work list (torch's caching allocator makes the
+    per-call allocation free of cudaMalloc / syncs), so two plans of one shape can be held and executed in any
+    order or on different streams.  shared_scratch=True reuses one shape-keyed scratch buffer instead: only for
+    callers that execute the plan immediately, on the same stream, before building the next one of that shape."""
     _need_cuda(block_map, row_sz, col_sz)
     BH, QC, KC = block_map.shape
     m = block_map.contiguous()
@@ -91,7 +96,8 @@ def plan_varblock(block_map: torch.Tensor, row_sz: torch.Tensor, col_sz: torch.T
     nbytes = C.c_size_t()
     check(lib().svgb_attn_plan_varblock_bytes(BH, S, QC, KC, C.byref(nbytes)), "plan_varblock_bytes")
     if ws is None:
-        ws = workspace(("vb", BH, S, QC, KC), nbytes.value, m.device)
+        ws = (workspace(("vb", BH, S, QC, KC), nbytes.value, m.device) if shared_scratch
+              else torch.empty(nbytes.value, dtype=torch.uint8, device=m.device))
     desc = Plan()
     fn = lib().svgb_attn_plan_varblock_gather if gather else lib().svgb_attn_plan_varblock
     check(fn(m.data_ptr(), r.data_ptr(), c.data_ptr(), BH, S, QC, KC, ws.data_ptr(), ws.numel(), C.byref(desc),
@@ -184,9 +190,12 @@ def attn_fwd_fp8(q8, k8, v8, q_scale, k_scale, v_scale, plan: AttnPlan, *, o_row
     if o_rows is not None:
         o_rows = o_rows.reshape(BH, S).to(torch.int32).contiguous()
     scale = float(D) ** -0.5 if sm_scale is None else float(sm_scale)
-    check(lib().svgb_attn_fwd_fp8(q8.contiguous().data_ptr(), k8.contiguous().data_ptr(), v8.contiguous().data_ptr(),
-                                  q_scale.contiguous().data_ptr(), k_scale.contiguous().data_ptr(),
-                                  v_scale.contiguous().data_ptr(), o.data_ptr(), _p(lse), _p(o_rows), BH, S, D,
+    # temporaries are bound to locals that outlive the launch call (a dropped .contiguous() copy could be recycled
+    # by the allocator for the next one and alias two operands)
+    q8c, k8c, v8c = q8.contiguous(), k8.contiguous(), v8.contiguous()
+    sqc, skc, svc = (t.to(torch.float32).contiguous() for t in (q_scale, k_scale, v_scale))
+    check(lib().svgb_attn_fwd_fp8(q8c.data_ptr(), k8c.data_ptr(), v8c.data_ptr(), sqc.data_ptr(), skc.data_ptr(),
+                                  svc.data_ptr(), o.data_ptr(), _p(lse), _p(o_rows), BH, S, D,
                                   D, S * D, D, S * D, scale, C.byref(plan.desc), plan.ws.data_ptr(), _stream(q8)),
           "svgb_attn_fwd_fp8")
     _bump()
@@ -293,10 +302,10 @@ def kmeans_assign(x, c, x_sq):
     _need_cuda(x, c, x_sq)
     BH, N, D = x.shape
     K = c.shape[1]
-    xc, cc = x.contiguous(), c.contiguous()
+    xc, cc, sqc = x.contiguous(), c.contiguous(), x_sq.to(torch.float32).contiguous()
     ws = _km_ws(BH, N, K, D, x.device)
     labels = torch.empty(BH, N, dtype=torch.int32, device=x.device)
-    check(lib().svgb_kmeans_assign(xc.data_ptr(), cc.data_ptr(), x_sq.contiguous().data_ptr(), labels.data_ptr(),
+    check(lib().svgb_kmeans_assign(xc.data_ptr(), cc.data_ptr(), sqc.data_ptr(), labels.data_ptr(),
                                    BH, N, K, D, _dt(x), ws.data_ptr(), ws.numel(), _stream(x)),
           "svgb_kmeans_assign")
     _bump(2)
@@ -308,11 +317,12 @@ def kmeans_update(x, labels, c_old):
     BH, N, D = x.shape
     K = c_old.shape[1]
     ws = _km_ws(BH, N, K, D, x.device)
-    c_new = torch.empty_like(c_old.contiguous())
+    xc, lc, cc = x.contiguous(), labels.to(torch.int32).contiguous(), c_old.contiguous()
+    c_new = torch.empty_like(cc)
     counts = torch.empty(BH, K, dtype=torch.int32, device=x.device)
     shift = torch.zeros(1, dtype=torch.float32, device=x.device)
-    check(lib().svgb_kmeans_update(x.contiguous().data_ptr(), labels.to(torch.int32).contiguous().data_ptr(),
-                                   c_old.contiguous().data_ptr(), c_new.data_ptr(), counts.data_ptr(),
+    check(lib().svgb_kmeans_update(xc.data_ptr(), lc.data_ptr(),
+                                   cc.data_ptr(), c_new.data_ptr(), counts.data_ptr(),
                                    shift.data_ptr(), BH, N, K, D, _dt(x), ws.data_ptr(), ws.numel(), _stream(x)),
           "svgb_kmeans_update")
     _bump(5)
@@ -330,7 +340,8 @@ def kmeans_run(x, init_centroids, max_iters, tol=1e-4):
     cents = torch.empty(BH, K, D, dtype=x.dtype, device=x.device)
     counts = torch.empty(BH, K, dtype=torch.int32, device=x.device)
     n_iter = torch.zeros(1, dtype=torch.int32, device=x.device)
-    check(lib().svgb_kmeans_run(x.contiguous().data_ptr(), init_centroids.contiguous().data_ptr(), BH, N, K, D,
+    xc, ic = x.contiguous(), init_centroids.contiguous()
+    check(lib().svgb_kmeans_run(xc.data_ptr(), ic.data_ptr(), BH, N, K, D,
                                 _dt(x), int(max_iters), float(tol), labels.data_ptr(), cents.data_ptr(),
                                 counts.data_ptr(), n_iter.data_ptr(), ws.data_ptr(), ws.numel(), _stream(x)),
           "svgb_kmeans_run")
@@ -344,8 +355,9 @@ def dynamic_map(qc, kc, k_sizes, top_p, preserve):
     BH, QC, D = qc.shape
     KC = kc.shape[1]
     out = torch.empty(BH, QC, KC, dtype=torch.uint8, device=qc.device)
-    check(lib().svgb_dynamic_map(qc.contiguous().data_ptr(), kc.contiguous().data_ptr(),
-                                 k_sizes.to(torch.int32).contiguous().data_ptr(), BH, QC, KC, D, _dt(qc),
+    qcc, kcc, ksc = qc.contiguous(), kc.contiguous(), k_sizes.to(torch.int32).contiguous()
+    check(lib().svgb_dynamic_map(qcc.data_ptr(), kcc.data_ptr(),
+                                 ksc.data_ptr(), BH, QC, KC, D, _dt(qc),
                                  float(top_p), int(preserve), out.data_ptr(), _stream(qc)), "svgb_dynamic_map")
     _bump()
     return out.view(torch.bool)
@@ -361,7 +373,8 @@ def sample_mse(q, k, v, rows, layout, ctx, F, P):
     ws = workspace(("smse", BH, S, D), nbytes.value, q.device)
     out = torch.empty(2, BH, dtype=torch.float32, device=q.device)
     r = rows.to(torch.int32).contiguous()
-    check(lib().svgb_sample_mse(q.contiguous().data_ptr(), k.contiguous().data_ptr(), v.contiguous().data_ptr(),
+    qc_, kc_, vc_ = q.contiguous(), k.contiguous(), v.contiguous()
+    check(lib().svgb_sample_mse(qc_.data_ptr(), kc_.data_ptr(), vc_.data_ptr(),
                                 r.data_ptr(), n, BH, S, D, _dt(q), int(layout), ctx, F, P, out.data_ptr(),
                                 ws.data_ptr(), ws.numel(), _stream(q)), "svgb_sample_mse")
     _bump(7)

@@ -187,6 +187,10 @@ class SVG1Core:
         if sampled_rows is None:
             sampled_rows = torch.randint(low=0, high=self.sample_mse_max_row, size=(min(self.num_sampled_rows, S),))
         rows_dev = sampled_rows.to(dev, non_blocking=True)
+        # slot reuse ACROSS calls: the staging buffers are still being read by the previous call's last head groups
+        # (queued on `cur`) and drained by its D2H copies -> this call's first H2D copies must wait for both
+        P_["h2d"].wait_stream(cur)
+        P_["h2d"].wait_stream(P_["d2h"])
         groups = [(g0, min(H, g0 + G)) for g0 in range(0, H, G)]
         ready, done_compute, done_d2h = {}, {}, {}
 

@@ -30,3 +30,22 @@ def kmeans_inputs(seed, B, N, D, K, clustered=True):
     idx = torch.randint(0, N, (B, K), generator=g)
     init = torch.gather(x, 1, idx[..., None].expand(-1, -1, D)).contiguous()
     return x, init
+
+
+def structured_qkv(seed, H, F, P, ctx, D, text_first=False, scale=1.5):
+    """q, k, v bf16 [1,H,S,D] whose heads clearly prefer one profiling mask: even heads attend inside their own FRAME
+    (spatial heads), odd heads to the same PATCH position across frames (temporal heads), so that best_mask_idx does
+    not hinge on bf16-vs-fp32 noise in sample_mse."""
+    g = torch.Generator().manual_seed(int(seed))
+    V, S = F * P, ctx + F * P
+    q, k, v = (torch.randn(1, H, S, D, generator=g) * 0.5 for _ in range(3))
+    v = v * 2
+    tok = torch.arange(V)
+    frame, patch = tok // P, tok % P
+    lo = ctx if text_first else 0
+    for h in range(H):
+        emb = torch.randn(max(F, P), D, generator=g) * scale
+        idx = frame if h % 2 == 0 else patch
+        q[0, h, lo:lo + V] += emb[idx]
+        k[0, h, lo:lo + V] += emb[idx]
+    return q.bfloat16(), k.bfloat16(), v.bfloat16()

@@ -125,3 +125,33 @@ def import_kernel_test(name):
     if tdir not in sys.path:
         sys.path.insert(0, tdir)
     return importlib.import_module(name)
+
+
+def reference_flashinfer_varblock(q, k, v, block_mask_map, block_row_sz, block_col_sz):
+    """The reference's live SVG2 attention call, svg.kmeans_utils.dynamic_block_sparse_fwd_flashinfer(..., is_cpu=False)
+    (svg/kmeans_utils.py:1319-1392).
+
+    The reference pins FlashInfer 0.2.10 + assets/patches/modifications.patch and resets two PRIVATE wrapper buffers
+    (`_vector_sparse_indices_buffer` / `_vector_sparse_indptr_buffer`, :1361-1366) that FlashInfer 0.6.x (this image)
+    no longer has, so the unmodified function raises AttributeError here.  In that case the same public-API sequence
+    is run without that one call: 512 MB float workspace, VariableBlockSparseAttentionWrapper(backend="auto"),
+    plan(block_mask_map, block_row_sz, block_col_sz, ...), run(q, k, v) — allocation, plan and run per call exactly
+    as the reference does every attention call.  Returns (o [B,H,S,D], how)."""
+    ku = import_kmeans_utils()
+    try:
+        return ku.dynamic_block_sparse_fwd_flashinfer(q, k, v, block_mask_map, block_row_sz, block_col_sz,
+                                                      is_cpu=False), "reference function, unmodified"
+    except AttributeError:
+        pass
+    import flashinfer
+    import torch
+
+    B, H, S, D = q.shape
+    qc_num, kc_num = block_row_sz.shape[-1], block_col_sz.shape[-1]
+    float_workspace_buffer = torch.empty(128 * 1024 * 1024, device=q.device)
+    wrapper = flashinfer.sparse.VariableBlockSparseAttentionWrapper(float_workspace_buffer, backend="auto")
+    wrapper.plan(block_mask_map=block_mask_map.reshape(B * H, qc_num, kc_num),
+                 block_row_sz=block_row_sz.reshape(B * H, qc_num), block_col_sz=block_col_sz.reshape(B * H, kc_num),
+                 num_qo_heads=B * H, num_kv_heads=B * H, head_dim=D, q_data_type=q.dtype, kv_data_type=k.dtype)
+    o = wrapper.run(q.reshape(B * H, S, D), k.reshape(B * H, S, D), v.reshape(B * H, S, D))
+    return o.reshape(B, H, S, D), "reference call sequence on FlashInfer 0.6.x (private-buffer reset skipped)"

@@ -1,0 +1,48 @@
+"""Helper launched by tests/test_configs_gpu.py::test_head_parallel_equals_single_gpu under torch.distributed.run
+(NCCL, one rank per GPU): every rank computes its interleaved share of the heads with sparse_core_head_parallel
+(multi-stream issue + overlapped per-head all-gather) and compares the gathered [1,H,S,D] tensor, bit for bit,
+with sparse_core over all heads on its own GPU."""
+import os
+import sys
+from pathlib import Path
+
+import torch
+import torch.distributed as dist
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT / "sparse-videogen_b200"))
+
+
+def main():
+    from svgb200.models import hyvideo as hy
+    from svgb200.parallel import HeadParallel, shard_heads
+
+    local = int(os.environ["LOCAL_RANK"])
+    world = int(os.environ["WORLD_SIZE"])
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    dist.init_process_group("nccl", device_id=dev)
+    H, F, P, ctx, plen, D = 4 * world, 6, 1200, 128, 40, 128
+    S = ctx + F * P
+    g = torch.Generator().manual_seed(0)  # identical inputs on every rank
+    q, k, v = (torch.randn(1, H, S, D, generator=g).to(torch.bfloat16).to(dev) for _ in range(3))
+    rows = torch.randint(0, 2000, (32,), generator=g)
+    core_obj = hy.HunyuanSVG1Core(ctx, plen, F, P, H, D, 0.35, dev, num_sampled_rows=32, sample_mse_max_row=2000)
+    ref = core_obj.sparse_core(q, k, v, sampled_rows=rows)
+    hp = HeadParallel()
+    ok = True
+    for rep in range(4):  # repeated: a stream-ordering bug shows up as run-to-run differences
+        out = core_obj.sparse_core_head_parallel(*(shard_heads(t, world, hp.rank) for t in (q, k, v)), hp,
+                                                 sampled_rows=rows)
+        torch.cuda.synchronize()
+        ok = ok and bool(torch.equal(out, ref))
+    flag = torch.tensor([1 if ok else 0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if hp.rank == 0:
+        print("HEAD_PARALLEL_OK" if int(flag.item()) == 1 else "HEAD_PARALLEL_MISMATCH", flush=True)
+    dist.destroy_process_group()
+    sys.exit(0 if int(flag.item()) == 1 else 1)
+
+
+if __name__ == "__main__":
+    main()
