@@ -219,6 +219,126 @@ def run_reference(args):
 # ---------------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------------
+def svg2_map(heads, seed=7, rho=0.30, QC=400, KC=1000, ctx=CTX, plen=PROMPT_LEN, video=F * P):
+    """The SVG2 shape of the same model: QC x KC Bernoulli(rho) map over uniform cluster sizes plus HunyuanVideo's prompt
+    / padding blocks (hyvideo/attention.py:681-697).  Returns (map [H,QC+t,KC+t] bool, row_sz, col_sz, flops)."""
+    gm = torch.Generator().manual_seed(seed)
+
+    def sizes(n):
+        b = torch.full((heads, n), video // n, dtype=torch.int32)
+        b[:, : video - (video // n) * n] += 1
+        return b
+
+    t = 2 if ctx else 0
+    row, col = sizes(QC), sizes(KC)
+    bm = torch.zeros(heads, QC + t, KC + t, dtype=torch.bool)
+    bm[:, :QC, :KC] = torch.rand(heads, QC, KC, generator=gm) < rho
+    if ctx:
+        extra = torch.tensor([[plen, ctx - plen]] * heads, dtype=torch.int32)
+        row, col = torch.cat([row, extra], 1), torch.cat([col, extra], 1)
+        bm[:, -2, :-1] = True   # prompt block <-> everything but the padding
+        bm[:, :-1, -2] = True
+        bm[:, -1, -1] = True
+    fl = 4.0 * D * (row.double()[:, :, None] * col.double()[:, None, :] * bm).sum().item()
+    return bm, row, col, fl
+
+
+def _time(fn, warm=2, iters=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(iters):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / iters
+
+
+def svg2_pipeline_probe(dev, model):
+    """Whole SVG2 core (k-means x2 -> dynamic map -> argsort x2 -> permute x3 -> plan -> attention with fused inverse
+    permutation) at a model's full shape, on tokens with cluster structure: per-stage CUDA-event times + the total of
+    a warm-started step call (2 Lloyd iterations, the reference's steady state)."""
+    from svgb200 import core, kmeans_utils as ku
+    from svgb200.models import hyvideo as hy, wan
+
+    if model == "hy":
+        Hh, ctx, Fm, Pm, QC, KC = 24, CTX, F, P, 400, 1000
+        sap = hy.HunyuanSAPCore(ctx, Fm, Pm, num_q_centroids=QC, num_k_centroids=KC, top_p_kmeans=0.9, min_kc_ratio=0.1,
+                                kmeans_iter_init=10, kmeans_iter_step=2, prompt_length=PROMPT_LEN)
+    else:
+        Hh, ctx, Fm, Pm, QC, KC = 40, 0, 21, 3600, 300, 1000
+        sap = wan.WanSAPCore(Fm, Pm, num_q_centroids=QC, num_k_centroids=KC, top_p_kmeans=0.9, min_kc_ratio=0.1,
+                             kmeans_iter_init=10, kmeans_iter_step=2)
+    V, Sm = Fm * Pm, ctx + Fm * Pm
+    g = torch.Generator(device=dev).manual_seed(11)
+    q, k, v = (torch.randn(1, Hh, Sm, D, device=dev, generator=g).to(torch.bfloat16) for _ in range(3))
+    base = torch.randn(1, Hh, 96, D, device=dev, generator=g) * 1.5
+    which = torch.randint(0, 96, (Sm,), device=dev, generator=g)
+    q = (q.float() * 0.7 + base[:, :, which]).to(torch.bfloat16)
+    k = (k.float() * 0.7 + base[:, :, which]).to(torch.bfloat16)
+    del base
+    sap.sparse_core(q, k, v)  # first call: k-means init
+    total = _time(lambda: sap.sparse_core(q, k, v), warm=1, iters=3)
+    last = sap.last
+    dyn, row_sz, col_sz, q_perm, k_perm = (last[x] for x in ("dynamic_map", "q_sizes", "k_sizes", "q_sorted_indices",
+                                                               "k_sorted_indices"))
+    qv = q[:, :, :V].reshape(Hh, V, D).contiguous()
+    kv = k[:, :, :V].reshape(Hh, V, D).contiguous()
+    qc0, kc0 = sap.state.q_centroids[sap.layer_idx], sap.state.k_centroids[sap.layer_idx]
+    st = {}
+    st["kmeans_q_2it"] = _time(lambda: ku.batch_kmeans_Euclid(qv, QC, max_iters=2, init_centroids=qc0), 1, 3)
+    st["kmeans_k_2it"] = _time(lambda: ku.batch_kmeans_Euclid(kv, KC, max_iters=2, init_centroids=kc0), 1, 3)
+    ql, qc, qs, _ = ku.batch_kmeans_Euclid(qv, QC, max_iters=2, init_centroids=qc0)
+    kl, kc, ks, _ = ku.batch_kmeans_Euclid(kv, KC, max_iters=2, init_centroids=kc0)
+    st["dynamic_map"] = _time(lambda: ku.identify_dynamic_map(qc[None], kc[None], qs[None], ks[None], 0.9, 0.1), 1, 3)
+    st["argsort_x2"] = _time(lambda: (core.argsort_labels(ql, QC), core.argsort_labels(kl, KC)), 1, 3)
+    st["permute_x3"] = _time(lambda: (core.permute_gather(q, q_perm), core.permute_gather(k, k_perm),
+                                      core.permute_gather(v, k_perm)), 1, 3)
+    qp, kp, vp = core.permute_gather(q, q_perm), core.permute_gather(k, k_perm), core.permute_gather(v, k_perm)
+    st["plan"] = _time(lambda: core.plan_varblock(dyn, row_sz, col_sz, Sm), 1, 3)
+    plan = core.plan_varblock(dyn, row_sz, col_sz, Sm)
+    st["attention"] = _time(lambda: core.attn_fwd(qp, kp, vp, plan, o_rows=q_perm), 1, 3)
+    fl = 4.0 * D * (row_sz.double()[:, :, None] * col_sz.double()[:, None, :] * dyn).sum().item()
+    return {"shape": f"H={Hh} S={Sm} QC={QC} KC={KC} top_p=0.9 (k-means on clustered synthetic tokens)",
+            "density": fl / (4.0 * D * Hh * Sm * Sm), "step_call_ms": total, "stages_ms": st,
+            "front_half_ms": total - st["attention"], "attention_tflops": fl / st["attention"] / 1e9,
+            "step_tflops": fl / total / 1e9}
+
+
+def fp8_density_sweep(dev, world, rank, dist):
+    """BASELINE configs[4]: Wan 2.1 720p SVG2 shape (S = 75 600, 40 heads, QC = 300 / KC = 1000), bf16 vs FP8 (e4m3)
+    variable-block attention at block densities 10-50 %.  Heads are sharded over the ranks (5 per GPU at N = 8); times
+    are the max over ranks, TFLOP/s whole-job."""
+    from svgb200 import core
+
+    Hw, Fw, Pw = 40, 21, 3600
+    Sw = Fw * Pw
+    if Hw % world:
+        return {"skipped": f"{Hw} heads do not divide over {world} ranks"}
+    Hl = Hw // world
+    g = torch.Generator(device=dev).manual_seed(100 + rank)
+    q, k, v = (torch.randn(1, Hl, Sw, D, device=dev, generator=g).to(torch.bfloat16) for _ in range(3))
+    (q8, sq), (k8, sk), (v8, sv) = (core.quantize_e4m3(x) for x in (q, k, v))
+    rows = []
+    for rho in (0.1, 0.2, 0.3, 0.4, 0.5):
+        bm, row, col, fl = svg2_map(Hl, seed=int(rho * 100) + rank, rho=rho, QC=300, KC=1000, ctx=0, plen=0, video=Sw)
+        plan = core.plan_varblock(bm.to(dev), row.to(dev), col.to(dev), Sw)
+        ms16 = _time(lambda: core.attn_fwd(q, k, v, plan), 1, 3)
+        ms8 = _time(lambda: core.attn_fwd_fp8(q8, k8, v8, sq, sk, sv, plan), 1, 3)
+        t = torch.tensor([ms16, ms8, fl], device=dev, dtype=torch.float64)
+        if world > 1:
+            tm = t.clone()
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            ms16, ms8, fl = tm[0].item(), tm[1].item(), t[2].item()
+        rows.append({"density": rho, "bf16_ms": ms16, "fp8_ms": ms8, "bf16_tflops": fl / ms16 / 1e9,
+                     "fp8_tflops": fl / ms8 / 1e9, "fp8_speedup": ms16 / ms8})
+    return {"shape": f"Wan 2.1 720p SVG2: S={Sw}, {Hw} heads ({Hl}/GPU), QC=300 KC=1000 Bernoulli maps, uniform sizes",
+            "n_gpus": world, "sweep": rows}
+
+
 def run_ours(args):
     import torch.distributed as dist
 
@@ -235,6 +355,7 @@ def run_ours(args):
     core.device_check()
     assert H_TOTAL % world == 0, "heads must divide across ranks"
     Hl = H_TOTAL // world
+    t_wall0 = time.time()
 
     # synthetic inputs: head h is generated from seed + h so results are identical for any N
     def make(seed_off):
@@ -260,12 +381,13 @@ def run_ours(args):
     gathered = torch.empty(1, H_TOTAL, S, D, dtype=torch.bfloat16, device=dev) if world > 1 else None
     attn_ev = []
 
-    def step(timed=False):
-        rows = torch.randint(0, SAMPLE_MAX_ROW, (N_SAMPLED_ROWS,), generator=gen)
+    def step(timed=False, rows=None, trace=None):
+        if rows is None:
+            rows = torch.randint(0, SAMPLE_MAX_ROW, (N_SAMPLED_ROWS,), generator=gen)
         if world > 1:
             # per-head attention, each head's output all-gather overlapped with the next head's compute
             return proc.sparse_core_head_parallel(q, k, v, hp, sampled_rows=rows, out=gathered,
-                                                  attn_events=attn_ev if timed else None)
+                                                  attn_events=attn_ev if timed else None, trace=trace)
         return proc.sparse_core(q, k, v, sampled_rows=rows, attn_events=attn_ev if timed else None)
 
     def barrier():
@@ -295,28 +417,59 @@ def run_ours(args):
     else:
         # per-head launches overlap across streams in the step, so time the dominant kernel on its own:
         # one launch over all local heads (same plan, same inputs), CUDA events on its stream
-        core.attn_fwd(q, k, v, proc.block_mask.plan)
-        torch.cuda.synchronize()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for _ in range(3):
-            core.attn_fwd(q, k, v, proc.block_mask.plan)
-        b.record()
-        torch.cuda.synchronize()
-        attn_ms = a.elapsed_time(b) / 3
+        attn_ms = _time(lambda: core.attn_fwd(q, k, v, proc.block_mask.plan), 1, 3)
     t = torch.tensor([ms_total, attn_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_step = t[0].item() / args.steps
     attn_ms = t[1].item()
 
-    # ---- e2e: pinned host buffers -> H2D -> step -> D2H of the result, through the public API
+    # ---- output checksum on FIXED sampled rows: must be identical for every N (heads are generated per global id,
+    # per-head computation does not depend on the sharding) -> compare across the lines of a scaling run
+    fixed_rows = torch.randint(0, SAMPLE_MAX_ROW, (N_SAMPLED_ROWS,), generator=torch.Generator().manual_seed(4321))
+    o_full = step(rows=fixed_rows)
+    torch.cuda.synchronize()
+    if world == 1:
+        o_all = o_full
+    else:
+        o_all = gathered
+    cs = o_all.double()
+    checksum = {"sum": cs.sum().item(), "abs_sum": cs.abs().sum().item(),
+                "per_head_sum_first3": [cs[0, h].sum().item() for h in range(3)],
+                "note": "fixed sampled rows (seed 4321); equal across N => the gathered [1,24,S,D] output is the same"}
+    del cs, o_full
+
+    # ---- N > 1: per-rank stage timeline of one step (event stamps), gathered to rank 0
+    timeline = None
+    if world > 1:
+        tr = {}
+        step(rows=fixed_rows, trace=tr)
+        torch.cuda.synchronize()
+        mine = {"rank": rank, "prologue_ms(sample_mse+placement)": tr["t0"].elapsed_time(tr["start"]),
+                "head_compute_done_ms": [tr["t0"].elapsed_time(e) for e in tr["compute_done"]],
+                "head_allgather_done_ms": [tr["t0"].elapsed_time(e) for e in tr["comm_done"]],
+                "end_ms": tr["t0"].elapsed_time(tr["end"])}
+        allr = [None] * world
+        dist.all_gather_object(allr, mine)
+        if rank == 0:
+            ends = [r["end_ms"] for r in allr]
+            last_c = [r["head_compute_done_ms"][-1] for r in allr]
+            timeline = {"per_rank": allr, "end_ms_max": max(ends), "end_ms_min": min(ends),
+                        "last_head_compute_done_ms_max": max(last_c),
+                        "exposed_allgather_ms(max end - max last compute)": max(ends) - max(last_c),
+                        "attention_alone_ms(one launch, all local heads)": attn_ms,
+                        "note": "ms since the step began on each rank; heads alternate over two compute streams, each "
+                                "head's ncclAllGather follows on the communication stream"}
+
+    # ---- e2e: pinned host buffers -> H2D -> step -> D2H of the result, through the public API.  N > 1: every head
+    # group's output is also all-gathered on the device (same pipeline as `value`); D2H returns the local heads.
     hq, hk, hv = (x.cpu().pin_memory() for x in (q, k, v))
     ho = torch.empty(1, Hl, S, D, dtype=torch.bfloat16).pin_memory()
+    hps = 2 if Hl >= 12 else 1
 
     def e2e_step():
         rows = torch.randint(0, SAMPLE_MAX_ROW, (N_SAMPLED_ROWS,), generator=gen)
-        proc.sparse_core_from_host(hq, hk, hv, ho, sampled_rows=rows)
+        proc.sparse_core_from_host(hq, hk, hv, ho, sampled_rows=rows, heads_per_stage=hps, hp=hp, gathered=gathered)
 
     e2e_steps = max(2, min(args.steps, 5))
     e2e_step()
@@ -335,60 +488,25 @@ def run_ours(args):
     # ---- SVG2 variable-block kernel at rho = 0.30 (reported beside the headline)
     svg2 = None
     if rank == 0:
-        QC, KC = 400, 1000
-        Sv = F * P
-        gm = torch.Generator().manual_seed(7)
-
-        def sizes(n, total):
-            b = torch.full((Hl, n), total // n, dtype=torch.int32)
-            b[:, : total - (total // n) * n] += 1
-            return b
-
-        row = torch.cat([sizes(QC, Sv), torch.tensor([[PROMPT_LEN, CTX - PROMPT_LEN]] * Hl, dtype=torch.int32)], 1)
-        col = torch.cat([sizes(KC, Sv), torch.tensor([[PROMPT_LEN, CTX - PROMPT_LEN]] * Hl, dtype=torch.int32)], 1)
-        bm = torch.zeros(Hl, QC + 2, KC + 2, dtype=torch.bool)
-        bm[:, :QC, :KC] = torch.rand(Hl, QC, KC, generator=gm) < 0.30
-        bm[:, -2, :-1] = True   # prompt block <-> everything but the padding (attention.py:681-684)
-        bm[:, :-1, -2] = True
-        bm[:, -1, -1] = True
-        fl = 4.0 * D * (row.double()[:, :, None] * col.double()[:, None, :] * bm).sum().item()
+        bm, row, col, fl = svg2_map(Hl)
         plan = core.plan_varblock(bm.to(dev), row.to(dev), col.to(dev), S)
-        for _ in range(2):
-            core.attn_fwd(q, k, v, plan)
-        torch.cuda.synchronize()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        n_it = 3
-        for _ in range(n_it):
-            core.attn_fwd(q, k, v, plan)
-        b.record()
-        torch.cuda.synchronize()
-        ms = a.elapsed_time(b) / n_it
-        svg2 = {"workload": f"variable-block map QC={QC}+2 KC={KC}+2 Bernoulli(0.30), uniform cluster sizes, {Hl} heads",
+        ms = _time(lambda: core.attn_fwd(q, k, v, plan), 2, 3)
+        pk_ = peaks()
+        svg2 = {"workload": f"variable-block map QC=400+2 KC=1000+2 Bernoulli(0.30), uniform cluster sizes, {Hl} heads",
                 "ms_per_call": ms, "tflops": fl / ms / 1e9, "density": fl / (4.0 * D * Hl * S * S),
+                "frac_of_sustained": fl / ms / 1e9 / pk_["sustained"] if pk_["sustained"] else None,
                 "dense_equiv_tflops": 4.0 * D * Hl * S * S / ms / 1e9}
+        del plan
 
     # ---- FP8 (e4m3) variant of the same band-mask attention (BASELINE config 5 flavour), reported beside it
     fp8 = None
     if rank == 0:
         try:
             (q8, sq), (k8, sk), (v8, sv) = (core.quantize_e4m3(x) for x in (q, k, v))
-            for _ in range(2):
-                core.attn_fwd_fp8(q8, k8, v8, sq, sk, sv, proc.block_mask.plan)
-            torch.cuda.synchronize()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            for _ in range(3):
-                core.attn_fwd_fp8(q8, k8, v8, sq, sk, sv, proc.block_mask.plan)
-            b.record()
-            torch.cuda.synchronize()
-            ms8 = a.elapsed_time(b) / 3
-            a.record()
-            core.quantize_e4m3(q)
-            b.record()
-            torch.cuda.synchronize()
+            ms8 = _time(lambda: core.attn_fwd_fp8(q8, k8, v8, sq, sk, sv, proc.block_mask.plan), 2, 3)
+            msq = _time(lambda: core.quantize_e4m3(q), 1, 2)
             fp8 = {"workload": f"same band mask, e4m3 Q/K/V (per-head scales), bf16 out, {Hl} heads", "ms_per_call": ms8,
-                   "tflops": flops_local / ms8 / 1e9, "quantize_ms_per_tensor": a.elapsed_time(b)}
+                   "tflops": flops_local / ms8 / 1e9, "quantize_ms_per_tensor": msq}
             del q8, k8, v8
         except Exception as e:  # noqa: BLE001
             fp8 = {"error": repr(e)[:200]}
@@ -405,18 +523,9 @@ def run_ours(args):
             def prep_call():
                 core.qkv_prep(qi, ki, vi, Hl, out=outs, norm=core.NORM_RMS_HEAD, gamma_q=gq, gamma_k=gk, eps=1e-6, rope=1,
                               cos=cos, sin=sin, rope_lo=0, rope_n=S - CTX)
-            for _ in range(2):
-                prep_call()
-            torch.cuda.synchronize()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            for _ in range(5):
-                prep_call()
-            b.record()
-            torch.cuda.synchronize()
-            msp = a.elapsed_time(b) / 5
+            msp = _time(prep_call, 2, 5)
             nbytes = 6 * Hl * S * D * 2
-            hbm = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()).get("hbm_gbs") if (ROOT / "MEASURED_PEAKS.json").exists() else None
+            hbm = peaks()["hbm"]
             prep = {"workload": f"[1,S,{Hl}x{D}] q,k,v -> [1,{Hl},S,{D}]: transpose + per-head RMSNorm(q,k) + RoPE (text last)",
                     "ms_per_call": msp, "algorithmic_bytes": nbytes, "gbs": nbytes / msp / 1e6,
                     "hbm_peak_gbs": hbm, "frac": (nbytes / msp / 1e6 / hbm) if hbm else None}
@@ -424,18 +533,60 @@ def run_ours(args):
         except Exception as e:  # noqa: BLE001
             prep = {"error": repr(e)[:200]}
 
+    del q, k, v, gathered
+    torch.cuda.empty_cache()
+
+    # ---- BASELINE configs[4]: FP8 density sweep at the Wan shape (all ranks: heads sharded)
+    fp8_sweep = None
+    if not args.no_extras:
+        try:
+            fp8_sweep = fp8_density_sweep(dev, world, rank, dist)
+        except Exception as e:  # noqa: BLE001
+            fp8_sweep = {"error": repr(e)[:300]}
+        torch.cuda.empty_cache()
+
     if rank != 0:
         if world > 1:
+            dist.barrier()
             dist.destroy_process_group()
         return
 
+    # ---- BASELINE configs[2] + the SVG2 front half: whole SAP core per stage at the HY and Wan shapes (N = 1 only)
+    svg2_pipeline = None
+    if world == 1 and not args.no_extras:
+        svg2_pipeline = {}
+        for model in ("hy", "wan"):
+            try:
+                svg2_pipeline[model] = svg2_pipeline_probe(dev, model)
+            except Exception as e:  # noqa: BLE001
+                svg2_pipeline[model] = {"error": repr(e)[:300]}
+            torch.cuda.empty_cache()
+
+    # ---- the reference's own GPU paths on this box (north_star: >= 1.5x), as a subprocess under a timeout
+    ref_gpu = None
+    if world == 1 and not args.no_ref_gpu and not args.no_extras:
+        try:
+            r = subprocess.run([sys.executable, str(ROOT / "tools" / "ref_gpu_paths.py"), "--heads", str(H_TOTAL)],
+                               capture_output=True, text=True, timeout=args.ref_gpu_timeout)
+            for ln in r.stdout.splitlines():
+                if ln.startswith("REF_GPU_JSON "):
+                    ref_gpu = json.loads(ln[len("REF_GPU_JSON "):])
+            if ref_gpu is None:
+                ref_gpu = {"error": "no result", "rc": r.returncode, "stderr_tail": r.stderr[-400:]}
+        except subprocess.TimeoutExpired:
+            ref_gpu = {"error": f"timed out after {args.ref_gpu_timeout} s"}
+        except Exception as e:  # noqa: BLE001
+            ref_gpu = {"error": repr(e)[:300]}
+
     pk = peaks()
     achieved = flops_local / attn_ms / 1e9 if attn_ms > 0 else None
-    traffic = None
+    traffic, traffic_src = None, None
     tj = ROOT / "profiles" / "attn_traffic.json"
     if tj.exists():
         try:
-            traffic = json.loads(tj.read_text()).get("dram_bytes_per_launch")
+            tjd = json.loads(tj.read_text())
+            traffic = tjd.get("dram_bytes_per_launch")
+            traffic_src = "profiles/attn_traffic.json (" + str(tjd.get("source", "ncu --set full capture")) + "); not measured in this run"
         except Exception:
             traffic = None
     tf_cpu, dt_cpu, sample, cores = cpu_naive_sample(rows=4096, seconds=12.0)
@@ -454,16 +605,24 @@ def run_ours(args):
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": pk["sustained"], "unit": "TFLOP/s",
                      "frac": (achieved / pk["sustained"]) if achieved and pk["sustained"] else None,
                      "frac_of_burst": (achieved / pk["burst"]) if achieved and pk["burst"] else None,
-                     "peak_src": pk["src"] + ", sustained (kernel runs ~60 ms back to back)",
-                     "kernel": "svgb::attn_fwd_kernel<128,true>", "traffic": traffic},
+                     "peak_src": pk["src"] + ", sustained (kernel runs ~50 ms back to back)",
+                     "kernel": "svgb::attn_fwd_kernel<128,DT_BF16>", "traffic": traffic, "traffic_src": traffic_src},
         "cpu_baseline": {"value": tf_cpu, "unit": "TFLOP/s", "cores": cores, "kind": "port", "sample": sample,
-                         "seconds": dt_cpu},
+                         "seconds": dt_cpu,
+                         "bound_by": "the naive formulation itself: it computes all S keys for every sampled query row, "
+                                     "builds the boolean mask and masked_fill's a [256, 119056] fp32 score block before "
+                                     "the softmax; only the allowed pairs are credited as FLOPs"},
         "e2e": {"value": flops_total / e2e_ms / 1e9, "unit": "TFLOP/s", "ms_per_step": e2e_ms,
-                "h2d_bytes_per_step": bytes_in, "d2h_bytes_per_step": bytes_out},
-        "clocks": clocks, "gpu_launches": launches, "svg2": svg2, "fp8": fp8, "prep": prep,
+                "h2d_bytes_per_step": bytes_in, "d2h_bytes_per_step": bytes_out,
+                "note": "per rank: H2D of its heads' Q,K,V, compute, (N>1: device all-gather of every head's output, as in "
+                        "`value`), D2H of its heads' output; 3-stream pipeline, heads_per_stage=%d" % hps},
+        "clocks": clocks, "gpu_launches": launches, "output_checksum": checksum, "scaling_timeline": timeline,
+        "svg2": svg2, "svg2_pipeline": svg2_pipeline, "fp8": fp8, "fp8_sweep": fp8_sweep, "prep": prep,
+        "ref_gpu": ref_gpu, "wall_s": time.time() - t_wall0,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
@@ -473,6 +632,9 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-extras", action="store_true", help="headline + roofline + e2e only (skip SVG2 pipeline, FP8 sweep, ref_gpu)")
+    ap.add_argument("--no-ref-gpu", action="store_true", help="skip timing the reference's own GPU paths")
+    ap.add_argument("--ref-gpu-timeout", type=float, default=420.0)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -84,6 +84,39 @@ def build_lib(force: bool = False, verbose: bool = False) -> Path:
     return LIB
 
 
+def build_variant(name: str, defines: list[str], verbose: bool = False) -> Path:
+    """Bring-up / A-B builds: the same sources with extra -D flags -> _lib/libsvgb200_<name>.so (select it with
+    SVGB200_LIB=<path>).  Not used by the product path."""
+    nvcc = _nvcc()
+    odir = OBJ_DIR / name
+    odir.mkdir(parents=True, exist_ok=True)
+
+    def compile_one(src: Path):
+        obj = odir / (src.stem + ".o")
+        cmd = [nvcc, *NVCC_FLAGS, *defines, "-c", str(src), "-o", str(obj)]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed for {src.name}:\n{r.stdout}\n{r.stderr}")
+        if verbose:
+            print(r.stderr)
+        return obj
+
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 2)) as ex:
+        objs = list(ex.map(compile_one, _sources()))
+    lib = OUT_DIR / f"libsvgb200_{name}.so"
+    r = subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static", "-o", str(lib),
+                        *map(str, objs)], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    return lib
+
+
 if __name__ == "__main__":
-    p = build_lib(force="--force" in sys.argv, verbose="-v" in sys.argv)
-    print(p)
+    if "--variant" in sys.argv:
+        i = sys.argv.index("--variant")
+        print(build_variant(sys.argv[i + 1], [a for a in sys.argv[i + 2:] if a.startswith("-D")], verbose="-v" in sys.argv))
+    else:
+        p = build_lib(force="--force" in sys.argv, verbose="-v" in sys.argv)
+        print(p)

@@ -361,17 +361,21 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
         for (int j = 0; j < nchunks; ++j) {
           const int b = j & 1;
           wait_full(2 * j + 1);
+          SVGB_TRACE(2, j, 0);
           mbar_wait(smem_u32(&bars->p_full[b]), (j >> 1) & 1, 5);
+          SVGB_TRACE(2, j, 1);
           tc_fence_after();
           issue_pv(b, (2 * j + 1) % kStages, chunk_n(j), j > 0);
           release(2 * j + 1);
           tc_commit(smem_u32(&bars->pv_done));
+          SVGB_TRACE(2, j, 2);
           if (j + 2 < nchunks) {
             wait_full(2 * j + 4);
             issue_qk(b, (2 * j + 4) % kStages, chunk_n(j + 2));
             tc_commit(smem_u32(&bars->s_full[b]));
             release(2 * j + 4);
           }
+          SVGB_TRACE(2, j, 3);
         }
         tc_commit(smem_u32(&bars->o_final));
       }
@@ -984,8 +988,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
           const uint32_t s_addr = lane_addr + (sb == 0 ? Cfg::kSCol0 : Cfg::kSCol1);
           const uint32_t o_addr = lane_addr + (t == 0 ? Cfg::kOCol0 : Cfg::kOCol1);
           const int q = q_row0 + t * kTileRows + row;
+#ifdef SVGB_ATTN_TRACE
+          const int tj = ntiles == 1 ? j : 2 * j + t;  // trace slot: (chunk, tile) steps in execution order
+#endif
+          SVGB_TRACE(half, tj, 0);
           mbar_wait(smem_u32(&bars->s_full[sb]), ntiles == 1 ? ((j >> 1) & 1) : (j & 1), 8 + t);
           tc_fence_after();
+          SVGB_TRACE(half, tj, 1);
 
           float rs;
           auto chunk_body = [&](auto plain_tag) {
@@ -994,6 +1003,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
             if (kPlain || mycols > 0) tmem_ld32(s_addr + c0, ra);
             if (kPlain || mycols > 32) tmem_ld32(s_addr + c0 + 32, rb);
             tc_wait_ld();
+            SVGB_TRACE(half, tj, 2);
             if constexpr (!kPlain) {
               auto sanitize = [&](uint32_t(&rr)[32], int g) {  // g: global 32-column group index (0..3)
                 const int left = valid - g * 32;
@@ -1021,6 +1031,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
               for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(rb[i]));
             }
             const float m_new = fmaxf(m_used[t], fmaxf(mx, exchange(mx)));
+            SVGB_TRACE(half, tj, 3);
             // lazy rescale: keep the stale reference max unless it grew by more than tau (log2 units)
             float alpha = 1.f;
             if ((m_new - m_used[t]) * c > kTau) {  // false when both are -inf (NaN compare)
@@ -1090,6 +1101,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
             };
             group_p(ra, 2 * half);
             group_p(rb, 2 * half + 1);
+            SVGB_TRACE(half, tj, 4);
             float s0, s1;
             unpack_f32x2(sum2, s0, s1);
             rs = s0 + s1;
@@ -1099,8 +1111,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
 
           l_run[t] += rs;
           tc_wait_st();
+          SVGB_TRACE(half, tj, 5);
           tc_fence_before();
           mbar_arrive(smem_u32(&bars->p_full[sb]));
+          SVGB_TRACE(half, tj, 6);
         }
       }
 

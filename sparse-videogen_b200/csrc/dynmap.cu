@@ -5,7 +5,13 @@
 //   scores = round16(round16(qc . kc) / float(sqrt(D)))          (matmul then `/`, :877)
 //   prob   = round16(w * exp(s - max) / max(sum, 1e-12))         (weighted_softmax, :852-861, fp32 inside)
 //   sort descending; ties -> lower column first (the reference's torch.sort is unstable; we pin it)
-//   cums   = round16(fp32 running sum) per position              (torch.cumsum on a 16-bit tensor)
+//   cums   = torch.cumsum of the sorted 16-bit tensor AS THE CUDA BACKEND COMPUTES IT (the reference runs on the
+//            GPU): blocks of 2*nx elements scanned by a Sklansky network in which every add rounds to 16 bit, block
+//            totals carried into element 0 of the next block (ATen/native/cuda/ScanUtils.cuh:
+//            tensor_kernel_scan_innermost_dim; nx from get_log_num_threads_x_inner_scan(rows, KC), 16 on this path).
+//            This is NOT an fp32 running sum: near p = 0.9 (bf16 spacing 2^-8) small probabilities are absorbed and
+//            the GPU keeps more clusters.  Reproduced bit for bit: maps recorded from the reference on a B200
+//            (tests/golden/kmeans_golden.npz, 800 x 1000) match exactly.
 //   keep[t] = t == 0 || !(cums[t-1] > round16(p)) || t < preserve   (:884-890; scalar compared in 16 bit)
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -43,7 +49,7 @@ __device__ __forceinline__ float block_reduce(float v, float* red, bool is_max) 
 template <bool BF16>
 __global__ void __launch_bounds__(256)
 dynmap_kernel(const uint16_t* __restrict__ qc, const uint16_t* __restrict__ kc, const int* __restrict__ k_sizes,
-              int QC, int KC, int KCpad, int D, float top_p, int preserve, uint8_t* __restrict__ map) {
+              int QC, int KC, int KCpad, int D, float top_p, int preserve, int log_nx, uint8_t* __restrict__ map) {
   extern __shared__ uint32_t smem[];
   uint32_t* keys = smem;                                  // KCpad
   float* sc = reinterpret_cast<float*>(keys + KCpad);     // KCpad : scores, then weighted exps
@@ -111,14 +117,59 @@ dynmap_kernel(const uint16_t* __restrict__ qc, const uint16_t* __restrict__ kc, 
       __syncthreads();
     }
   }
-  if (threadIdx.x == 0) {
-    const float p16 = h2f<BF16>(f2h<BF16>(top_p));
-    float acc = 0.f, prev = 0.f;
-    for (int t = 0; t < KC; ++t) {
-      keep[t] = (t == 0) || !(prev > p16) || (t < preserve);
-      acc += h2f<BF16>(static_cast<uint16_t>(keys[t] >> 16));
-      prev = h2f<BF16>(f2h<BF16>(acc));
+  // ---- cumsum exactly as torch's CUDA scan does it on a 16-bit tensor (see the header comment); cums -> sc[]
+  auto r16 = [](float f) { return h2f<BF16>(f2h<BF16>(f)); };
+  if (log_nx == 4) {
+    // 32-element blocks: one warp, lane = element, Sklansky steps through shuffles; blocks are a serial chain
+    if (threadIdx.x < 32) {
+      const int lane = threadIdx.x;
+      float total = 0.f;
+      for (int b0 = 0; b0 < KC; b0 += 32) {
+        const int t = b0 + lane;
+        float v = t < KC ? h2f<BF16>(static_cast<uint16_t>(keys[t] >> 16)) : 0.f;
+        if (lane == 0) v = r16(v + total);
+#pragma unroll
+        for (int m = 0; m < 5; ++m) {
+          const int sft = 1 << m;
+          const float o = __shfl_sync(0xffffffffu, v, (lane & ~(2 * sft - 1)) | (sft - 1));
+          if (lane & sft) v = r16(v + o);
+        }
+        if (t < KC) sc[t] = v;
+        total = __shfl_sync(0xffffffffu, v, 31);
+      }
     }
+  } else {
+    // general block size 2 * nx (64 .. 1024): the same network in shared memory
+    const int nx = 1 << log_nx, blk = 2 * nx;
+    float* buf = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(keep + KCpad) + 15) & ~uintptr_t(15));
+    float total = 0.f;
+    for (int b0 = 0; b0 < KC; b0 += blk) {
+      for (int e = threadIdx.x; e < blk; e += blockDim.x) {
+        float v = (b0 + e) < KC ? h2f<BF16>(static_cast<uint16_t>(keys[b0 + e] >> 16)) : 0.f;
+        if (e == 0) v = r16(v + total);
+        buf[e] = v;
+      }
+      __syncthreads();
+      for (int m = 0; m <= log_nx; ++m) {
+        const int sft = 1 << m;
+        for (int tt = threadIdx.x; tt < nx; tt += blockDim.x) {
+          const int a = ((tt >> m) << (m + 1)) | sft;
+          const int ti = a + (tt % sft), si = a - 1;
+          buf[ti] = r16(buf[ti] + buf[si]);
+        }
+        __syncthreads();
+      }
+      for (int e = threadIdx.x; e < blk; e += blockDim.x)
+        if (b0 + e < KC) sc[b0 + e] = buf[e];
+      total = buf[blk - 1];
+      __syncthreads();
+    }
+  }
+  __syncthreads();
+  {
+    const float p16 = r16(top_p);
+    for (int t = threadIdx.x; t < KC; t += blockDim.x)
+      keep[t] = (t == 0) || !(sc[t - (t > 0)] > p16) || (t < preserve);
   }
   __syncthreads();
   uint8_t* out = map + (static_cast<size_t>(bh) * QC + i) * KC;
@@ -137,17 +188,25 @@ extern "C" int svgb_dynamic_map(const void* qc, const void* kc, const int32_t* k
   SVGB_REQUIRE(dtype == SVGB_BF16 || dtype == SVGB_F16, "dtype %d unsupported", dtype);
   int KCpad = 2;
   while (KCpad < KC) KCpad <<= 1;
-  const size_t smem = sizeof(uint32_t) * KCpad + sizeof(float) * (KCpad + D + 32) + KCpad;
+  // block size of torch's CUDA scan for a [BH*QC, KC] tensor: get_log_num_threads_x_inner_scan (ScanUtils.cuh:19-41,
+  // uint32 arithmetic) -- 4 (32-element blocks) for every shape on this path
+  uint32_t lx = 0, ly = 0;
+  while ((1u << lx) < static_cast<uint32_t>(KC)) ++lx;
+  while ((1ull << ly) < static_cast<unsigned long long>(BH) * QC) ++ly;
+  uint32_t log_nx = (9u + lx - ly) / 2u;
+  log_nx = log_nx < 4u ? 4u : (log_nx > 9u ? 9u : log_nx);
+  const size_t smem = sizeof(uint32_t) * KCpad + sizeof(float) * (KCpad + D + 32) + KCpad +
+                      (log_nx == 4 ? 0 : sizeof(float) * (2u << log_nx) + 16);
   dim3 grid(QC, BH);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (dtype == SVGB_BF16) {
     SVGB_CUDA(cudaFuncSetAttribute(dynmap_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dynmap_kernel<true><<<grid, 256, smem, st>>>(static_cast<const uint16_t*>(qc), static_cast<const uint16_t*>(kc),
-                                                 k_sizes, QC, KC, KCpad, D, top_p, preserve, map);
+                                                 k_sizes, QC, KC, KCpad, D, top_p, preserve, static_cast<int>(log_nx), map);
   } else {
     SVGB_CUDA(cudaFuncSetAttribute(dynmap_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dynmap_kernel<false><<<grid, 256, smem, st>>>(static_cast<const uint16_t*>(qc), static_cast<const uint16_t*>(kc),
-                                                  k_sizes, QC, KC, KCpad, D, top_p, preserve, map);
+                                                  k_sizes, QC, KC, KCpad, D, top_p, preserve, static_cast<int>(log_nx), map);
   }
   SVGB_LAUNCH_OK();
   return 0;

@@ -318,7 +318,11 @@ kmeans_update_kernel(const uint16_t* __restrict__ x, const int* __restrict__ per
 }
 
 // |c|^2 of the centroid buffer selected by the loop state, written in the padded [BH, Kpad] layout
-// the assign kernel bulk-copies (fp32 sum of 16-bit-rounded squares, _euclid_assign_kernel:531).
+// the assign kernel bulk-copies.  The reference computes it as `tl.sum(c_tile * c_tile, axis=0)` on 16-bit tiles
+// (_euclid_assign_kernel, svg/kmeans_utils.py:531): products AND the reduction live in the 16-bit type, in a
+// layout-dependent order (labels recorded from the reference's Triton kernel on a B200 are explained to the last
+// point by per-centroid offsets of a few bf16 ulps of |c|^2 -- tests/golden/kmeans_golden.npz).  We take the
+// correctly rounded value of that quantity: fp32 sum of the 16-bit-rounded squares, rounded once to the 16-bit type.
 template <bool BF16>
 __global__ void csq_kernel(const uint16_t* __restrict__ c0, const uint16_t* __restrict__ c1,
                            float* __restrict__ out, int K, int Kpad, int D, const KmState* __restrict__ state) {
@@ -341,7 +345,7 @@ __global__ void csq_kernel(const uint16_t* __restrict__ c0, const uint16_t* __re
     }
   }
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-  if (lane == 0) out[static_cast<size_t>(bh) * Kpad + k] = acc;
+  if (lane == 0) out[static_cast<size_t>(bh) * Kpad + k] = round16<BF16>(acc);
 }
 
 __global__ void km_commit_kernel(KmState* st, float* shift_max, float tol, int it) {

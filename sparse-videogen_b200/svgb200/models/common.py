@@ -140,13 +140,18 @@ class SVG1Core:
                                               self.frame_size)
         return out
 
-    def sparse_core_head_parallel(self, query, key, value, hp, sampled_rows=None, out=None, attn_events=None):
+    def sparse_core_head_parallel(self, query, key, value, hp, sampled_rows=None, out=None, attn_events=None,
+                                  trace=None):
         """Same as sparse_core on this rank's heads ([1, H_local, S, D]), with the output all-gather of every
         head issued on a side stream as soon as that head's attention + inverse placement finished, so the
         NVLink transfer of head i overlaps the attention of head i+1 (svgb200.parallel.HeadParallel).
         Returns the full [1, H_local * world, S, D] output (heads interleaved: global h = i*world + rank)."""
         cfg, Hl, S, D = query.shape
         assert cfg == 1
+        if trace is not None:
+            t0 = torch.cuda.Event(enable_timing=True)
+            t0.record()
+            trace["t0"] = t0
         sampled_mses = self.sample_mse(query, key, value, sampled_rows)
         best_mask_idx = torch.argmin(sampled_mses, dim=0)
         q_out, k_out, v_out = torch.empty_like(query), torch.empty_like(key), torch.empty_like(value)
@@ -166,12 +171,16 @@ class SVG1Core:
                                               self.num_frame, self.frame_size)
             return o
 
-        return hp.run_overlapped(one_head, Hl, S, D, query.dtype, query.device, out=out)
+        return hp.run_overlapped(one_head, Hl, S, D, query.dtype, query.device, out=out, trace=trace)
 
-    def sparse_core_from_host(self, hq, hk, hv, ho, sampled_rows=None, heads_per_stage=2):
+    def sparse_core_from_host(self, hq, hk, hv, ho, sampled_rows=None, heads_per_stage=2, hp=None, gathered=None):
         """End-to-end entry for callers whose Q/K/V live in (pinned) host memory: heads are streamed through
         a 3-stage pipeline — H2D copy of group g+1 | compute of group g | D2H copy of group g-1 — on three
-        CUDA streams, so the PCIe transfers hide behind the attention."""
+        CUDA streams, so the PCIe transfers hide behind the attention.
+
+        Head-parallel (hp = svgb200.parallel.HeadParallel, world > 1): hq/hk/hv/ho hold this rank's heads; each
+        group's output is additionally all-gathered into `gathered` [1, H_local*world, S, D] on the device (the
+        downstream projection needs every head) on hp's communication stream, overlapping the next group."""
         cfg, H, S, D = hq.shape
         assert cfg == 1
         dev = self.block_mask.plan.ws.device
@@ -192,7 +201,7 @@ class SVG1Core:
         P_["h2d"].wait_stream(cur)
         P_["h2d"].wait_stream(P_["d2h"])
         groups = [(g0, min(H, g0 + G)) for g0 in range(0, H, G)]
-        ready, done_compute, done_d2h = {}, {}, {}
+        ready, done_compute, done_d2h, gather_done = {}, {}, {}, {}
 
         def issue_h2d(gi):
             g0, g1 = groups[gi]
@@ -200,6 +209,8 @@ class SVG1Core:
             with torch.cuda.stream(P_["h2d"]):
                 if gi >= 2:
                     P_["h2d"].wait_event(done_d2h[gi - 2])  # slot reuse: its output must have left first
+                    if (gi - 2) in gather_done:
+                        P_["h2d"].wait_event(gather_done[gi - 2])
                 for dst, src in zip(slot[:3], (hq, hk, hv)):
                     dst[:, : g1 - g0].copy_(src[:, g0:g1], non_blocking=True)
                 ev = torch.cuda.Event()
@@ -218,6 +229,18 @@ class SVG1Core:
             ev = torch.cuda.Event()
             ev.record(cur)
             done_compute[gi] = ev
+            if hp is not None and hp.world > 1:
+                import torch.distributed as dist
+
+                comm, _ = hp.streams(dev)
+                with torch.cuda.stream(comm):
+                    comm.wait_event(ev)
+                    for i in range(n):
+                        dist.all_gather_into_tensor(gathered[0, (g0 + i) * hp.world:(g0 + i + 1) * hp.world],
+                                                    slot[3][0, i:i + 1], group=hp.group)
+                    evg = torch.cuda.Event()
+                    evg.record(comm)
+                gather_done[gi] = evg
             with torch.cuda.stream(P_["d2h"]):
                 P_["d2h"].wait_event(ev)
                 ho[:, g0:g1].copy_(slot[3][:, :n], non_blocking=True)
@@ -225,6 +248,8 @@ class SVG1Core:
                 ev2.record(P_["d2h"])
                 done_d2h[gi] = ev2
         cur.wait_stream(P_["d2h"])
+        if hp is not None and hp.world > 1:
+            cur.wait_stream(hp.streams(dev)[0])
         return ho
 
     def dense_core(self, query, key, value, cu_max_seqlens=None):

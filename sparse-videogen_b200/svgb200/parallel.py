@@ -33,6 +33,13 @@ class HeadParallel:
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self._comm_stream = None
 
+    def streams(self, device, compute_streams: int = 2):
+        """(communication stream, compute side streams), created on first use."""
+        if self._comm_stream is None:
+            self._comm_stream = torch.cuda.Stream(device=device)
+            self._compute_streams = [torch.cuda.Stream(device=device) for _ in range(max(1, compute_streams))]
+        return self._comm_stream, self._compute_streams
+
     def local_heads(self, num_heads: int):
         return owned_heads(num_heads, self.world, self.rank)
 
@@ -50,7 +57,8 @@ class HeadParallel:
         return out
 
     def run_overlapped(self, per_head_fn: Callable[[int], torch.Tensor], num_local_heads: int, S: int, D: int,
-                       dtype, device, out: Optional[torch.Tensor] = None, compute_streams: int = 2) -> torch.Tensor:
+                       dtype, device, out: Optional[torch.Tensor] = None, compute_streams: int = 2,
+                       trace: Optional[dict] = None) -> torch.Tensor:
         """per_head_fn(i) computes local head i ([S, D] or [1,1,S,D]) on the CURRENT stream.
 
         Heads are issued round-robin on `compute_streams` side streams, so the last partial wave of head i's
@@ -61,19 +69,21 @@ class HeadParallel:
         if out is None:
             out = torch.empty(1, H, S, D, dtype=dtype, device=device)
         cur = torch.cuda.current_stream(device)
-        if self._comm_stream is None:
-            self._comm_stream = torch.cuda.Stream(device=device)
-            self._compute_streams = [torch.cuda.Stream(device=device) for _ in range(max(1, compute_streams))]
-        start = torch.cuda.Event()
+        self.streams(device, compute_streams)
+        start = torch.cuda.Event(enable_timing=trace is not None)
         start.record(cur)
+        if trace is not None:  # event stamps for the per-rank stage timeline (bench.py `scaling_timeline`)
+            trace.update(start=start, compute_done=[], comm_done=[])
         keep = []
         for i in range(num_local_heads):
             cs = self._compute_streams[i % len(self._compute_streams)]
             with torch.cuda.stream(cs):
                 cs.wait_event(start)
                 o = per_head_fn(i).reshape(1, S, D)
-                ev = torch.cuda.Event()
+                ev = torch.cuda.Event(enable_timing=trace is not None)
                 ev.record(cs)
+            if trace is not None:
+                trace["compute_done"].append(ev)
             keep.append(o)
             if self.world == 1:
                 with torch.cuda.stream(cs):
@@ -82,9 +92,17 @@ class HeadParallel:
             with torch.cuda.stream(self._comm_stream):
                 self._comm_stream.wait_event(ev)
                 dist.all_gather_into_tensor(out[0, i * self.world:(i + 1) * self.world], o, group=self.group)
+                if trace is not None:
+                    evc = torch.cuda.Event(enable_timing=True)
+                    evc.record(self._comm_stream)
+                    trace["comm_done"].append(evc)
         for cs in self._compute_streams:
             cur.wait_stream(cs)
         cur.wait_stream(self._comm_stream)
         for o in keep:  # tensors were produced on side streams: tell the allocator the current stream uses them
             o.record_stream(cur)
+        if trace is not None:
+            end = torch.cuda.Event(enable_timing=True)
+            end.record(cur)
+            trace["end"] = end
         return out

@@ -49,3 +49,20 @@ def structured_qkv(seed, H, F, P, ctx, D, text_first=False, scale=1.5):
         q[0, h, lo:lo + V] += emb[idx]
         k[0, h, lo:lo + V] += emb[idx]
     return q.bfloat16(), k.bfloat16(), v.bfloat16()
+
+
+DM_CASES = {"hy": (2, 400, 1000, 128), "small": (3, 12, 40, 64)}
+
+
+def dm_inputs():
+    """Inputs of the GPU identify_dynamic_map goldens: {name: (qc, kc bf16 [1,H,*,D], k_sizes, q_sizes int32)}, drawn in
+    this order from one generator (seed 41)."""
+    g = torch.Generator().manual_seed(41)
+    out = {}
+    for name, (H, QC, KC, D) in DM_CASES.items():
+        qc = (torch.randn(1, H, QC, D, generator=g) * 1.5).bfloat16()
+        kc = (torch.randn(1, H, KC, D, generator=g) * 1.5).bfloat16()
+        ks = torch.randint(0, 300, (1, H, KC), generator=g, dtype=torch.int32)
+        qs = torch.randint(1, 300, (1, H, QC), generator=g, dtype=torch.int32)
+        out[name] = (qc, kc, ks, qs)
+    return out

@@ -1,7 +1,15 @@
-"""Dump the per-chunk timeline of one attention CTA (needs the SVGB_ATTN_TRACE build).  Bring-up tool."""
+"""Dump the per-chunk timeline of one attention CTA (needs a -DSVGB_ATTN_TRACE=<item> build: see build.py --variant).
+
+    python sparse-videogen_b200/build.py --variant trace0 -DSVGB_ATTN_TRACE=0
+    SVGB200_LIB=$PWD/sparse-videogen_b200/svgb200/_lib/libsvgb200_trace0.so TRACE_CASE=vb python tools/attn_trace.py
+
+TRACE_CASE: band (HY band plan, two-tile per-tile mapping) | aligned (single-tile items, full chunks) |
+            vb (QC=400 / KC=1000 uniform map: item 0 = 256-row two-tile item, item 1 = 41-row single-tile tail; shared
+            softmax mapping).  Output: gpurun_out/attn_trace_<case>_<tag>.json + a summary on stdout."""
 import ctypes as C
 import json
 import os
+import statistics as st
 import sys
 from pathlib import Path
 
@@ -17,9 +25,13 @@ dev = torch.device("cuda:0")
 H, S, D = 4, bench.S, bench.D
 q, k, v = (torch.randn(1, H, S, D, device=dev, dtype=torch.bfloat16) for _ in range(3))
 CASE = os.environ.get("TRACE_CASE", "band")
+TAG = os.environ.get("TRACE_TAG", "")
 if CASE == "band":
     W, _ = bench.band_width()
     plan = core.plan_band(core.MASK_HY, bench.F * bench.P, bench.F * bench.P + bench.PROMPT_LEN, W, H, S, dev)
+elif CASE == "vb":
+    bm, row, col, _ = bench.svg2_map(H)
+    plan = core.plan_varblock(bm.to(dev), row.to(dev), col.to(dev), S)
 else:  # aligned single-tile items, full 128-column chunks
     S = 128 * 930
     q, k, v = (x[:, :, :S].contiguous() for x in (q, k, v))
@@ -36,27 +48,27 @@ fn = _lib.lib().svgb_debug_attn_trace
 fn.argtypes = [C.POINTER(C.c_longlong), C.c_int]
 assert fn(buf, 1536) == 0
 tr = [[[buf[(r * 64 + j) * 8 + e] for e in range(8)] for j in range(64)] for r in range(3)]
-t0 = tr[2][2][0]
-out = {"roles": ["softmax_t0(warp4)", "softmax_t1(warp8)", "mma"],
-       "softmax_events": ["wait_S", "S_ready", "ld_done", "max_done", "exp_done", "st_done", "arrived"],
-       "mma_events": ["wait_P0", "P0_ready", "pv0_issued", "qk0_issued+commit", "P1_ready", "pv1_issued", "qk1_issued+commit"]}
-rows = []
-for j in range(2, 40):
-    rows.append({"j": j, "t0": [x - t0 for x in tr[0][j][:7]], "t1": [x - t0 for x in tr[1][j][:7]],
-                 "mma": [x - t0 for x in tr[2][j][:7]]})
-out["rows"] = rows
+t0 = min(x for x in tr[2][2] if x > 0) if any(tr[2][2]) else 0
+rows = [{"j": j, "w4": [x - t0 for x in tr[0][j][:7]], "w8": [x - t0 for x in tr[1][j][:7]],
+         "mma": [x - t0 for x in tr[2][j][:7]]} for j in range(2, 60)]
 (ROOT / "gpurun_out").mkdir(exist_ok=True)
-(ROOT / "gpurun_out" / "attn_trace.json").write_text(json.dumps(out))
-for r in rows[8:12]:
-    print(CASE, r["j"], "T0", r["t0"], "T1", r["t1"], "MMA", r["mma"])
-# summary: mean durations
-import statistics as st
-def d(role, a, b):
-    return st.mean(r[role][b] - r[role][a] for r in rows[4:36])
-print("softmax t0: wait", d("t0", 0, 1), "ld", d("t0", 1, 2), "max", d("t0", 2, 3), "exp", d("t0", 3, 4), "st", d("t0", 4, 5), "arrive", d("t0", 5, 6))
-print("softmax t1: wait", d("t1", 0, 1), "ld", d("t1", 1, 2), "max", d("t1", 2, 3), "exp", d("t1", 3, 4), "st", d("t1", 4, 5), "arrive", d("t1", 5, 6))
-if CASE == "band":
-    print("mma: waitP0", d("mma", 0, 1), "pv0", d("mma", 1, 2), "qk0", d("mma", 2, 3), "waitP1", d("mma", 3, 4), "pv1", d("mma", 4, 5), "qk1", d("mma", 5, 6))
-else:
-    print("mma: waitP0", d("mma", 0, 1), "pv0", d("mma", 1, 2), "qk0", d("mma", 2, 3))
-print("period", st.mean(rows[i + 1]["mma"][0] - rows[i]["mma"][0] for i in range(4, 34)))
+(ROOT / "gpurun_out" / f"attn_trace_{CASE}_{TAG}.json").write_text(json.dumps(
+    {"case": CASE, "tag": TAG, "softmax_events": ["wait_S", "S_ready", "ld_done", "max(+exchange)_done", "exp_done", "st_done", "arrived"],
+     "rows": rows}))
+
+
+def d(role, a, b, lo=6, hi=50):
+    xs = [r[role][b] - r[role][a] for r in rows[lo:hi] if r[role][a] > 0 and r[role][b] > 0]
+    return round(st.mean(xs), 1) if xs else None
+
+
+def period(role, ev, lo=6, hi=50):
+    xs = [rows[i + 1][role][ev] - rows[i][role][ev] for i in range(lo, hi) if rows[i][role][ev] > 0 and rows[i + 1][role][ev] > 0]
+    return round(st.mean(xs), 1) if xs else None
+
+
+for role in ("w4", "w8"):
+    print(CASE, TAG, role, "wait", d(role, 0, 1), "ld", d(role, 1, 2), "max", d(role, 2, 3), "exp", d(role, 3, 4), "st", d(role, 4, 5),
+          "arrive", d(role, 5, 6), "| step period", period(role, 0))
+print(CASE, TAG, "mma: waitP", d("mma", 0, 1), "issue1", d("mma", 1, 2), "issue2", d("mma", 2, 3), "e3-4", d("mma", 3, 4), "e4-5", d("mma", 4, 5),
+      "e5-6", d("mma", 5, 6), "| period", period("mma", 0))

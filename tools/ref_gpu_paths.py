@@ -1,18 +1,24 @@
-"""Time the REFERENCE's own GPU block-sparse attention paths on this B200, on the same synthetic inputs
-as our kernel (R-FI, R-FX).  Measurement tool only — nothing here is product code.
+"""Time the REFERENCE's own GPU block-sparse attention paths on this B200, on the same synthetic inputs as our
+kernel, and print ONE JSON object (bench.py runs this as a subprocess under a timeout and embeds the result as
+`ref_gpu`; `north_star`: ">= 1.5x the reference's own FlashInfer/Triton block-sparse path on the same B200").
 
-  R-FI  svg.kmeans_utils.dynamic_block_sparse_fwd_flashinfer = FlashInfer VariableBlockSparseAttentionWrapper
-        (svg/kmeans_utils.py:1319-1392), plan + run as the reference calls it every step, and run alone.
-        The image ships flashinfer 0.6.x (the reference vendors 0.2.10 + a patch; same wrapper API).
-  R-FX  torch.compile(flex_attention) with the reference HY BlockMask
-        (svg/models/hyvideo/attention.py:30,401-403,527-551; mask_mod hyvideo/utils.py:20-44).
+  R-FI  svg.kmeans_utils.dynamic_block_sparse_fwd_flashinfer (svg/kmeans_utils.py:1319-1392): the live SVG2 attention
+        call = scratch allocation + VariableBlockSparseAttentionWrapper.plan + .run, every call.  Executed from the
+        unmodified reference (baseline/_ref or /root/reference) through tests/golden/ref_import.py; on this image's
+        FlashInfer 0.6.x the reference's private-buffer reset no longer exists and is skipped (see ref_import).
+        `run_only` re-runs wrapper.run on an existing plan (what a reference that cached its plan would pay).
+  R-FX  the reference's compiled flex_attention with its own BlockMask: svg.models.hyvideo.attention
+        .prepare_flexattention + Hunyuan_SVGAttn_Processor2_0.sparse_flex_attention (hyvideo/attention.py:30,
+        401-403, 527-551; mask_mod hyvideo/utils.py:20-44) — the live SVG1 attention call.
 
-Writes JSON lines to gpurun_out/ref_gpu.jsonl.  Each section is wrapped so a failure (JIT unavailable
-offline, OOM...) is recorded instead of aborting the rest.
+Same inputs go through svgb200 for the ratio and the max-abs difference of the two outputs.  First calls (JIT /
+torch.compile) are excluded from the timings and reported separately.  Every section is wrapped so that a failure is
+recorded instead of aborting the rest; nothing here is product code.
+
+    python tools/ref_gpu_paths.py [--heads 24] [--skip-flex] [--budget-s 240]
 """
+import argparse
 import json
-import math
-import os
 import sys
 import time
 import traceback
@@ -23,22 +29,11 @@ import torch
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT / "sparse-videogen_b200"))
 sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests" / "golden"))
 import bench  # noqa: E402
 
-OUT = ROOT / "gpurun_out"
-OUT.mkdir(exist_ok=True)
-dev = torch.device("cuda:0")
-H = int(os.environ.get("REF_H", 24))
-S, D, F, P, CTX, PLEN = bench.S, bench.D, bench.F, bench.P, bench.CTX, bench.PROMPT_LEN
 
-
-def emit(**kw):
-    print(json.dumps(kw), flush=True)
-    with open(OUT / "ref_gpu.jsonl", "a") as f:
-        f.write(json.dumps(kw) + "\n")
-
-
-def timeit(fn, warm=2, iters=5):
+def timeit(fn, warm=1, iters=3):
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
@@ -54,122 +49,95 @@ def timeit(fn, warm=2, iters=5):
     return ts[len(ts) // 2]
 
 
-q, k, v = (torch.randn(1, H, S, D, device=dev, dtype=torch.bfloat16) for _ in range(3))
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--heads", type=int, default=24)
+    ap.add_argument("--skip-flex", action="store_true")
+    ap.add_argument("--budget-s", type=float, default=240.0)
+    args = ap.parse_args()
+    t_start = time.time()
+    dev = torch.device("cuda:0")
+    H, S, D, F, P, CTX, PLEN = args.heads, bench.S, bench.D, bench.F, bench.P, bench.CTX, bench.PROMPT_LEN
+    out = {"heads": H, "S": S, "D": D, "gpu": torch.cuda.get_device_name(0)}
+    import ref_import as R
 
-
-def varblock_inputs(QC, KC, rho, seed=0):
-    g = torch.Generator().manual_seed(seed)
-
-    def sizes(n):
-        b = torch.full((H, n), S // n, dtype=torch.int32)
-        b[:, : S - (S // n) * n] += 1
-        return b
-    row, col = sizes(QC), sizes(KC)
-    bm = torch.rand(H, QC, KC, generator=g) < rho
-    bm[:, :, 0] = True
-    fl = 4.0 * D * (row.double()[:, :, None] * col.double()[:, None, :] * bm).sum().item()
-    return bm, row, col, fl
-
-
-# ------------------------------------------------------------------------------------------ ours
-try:
+    out["reference_root"] = R.reference_root()
+    g = torch.Generator(device=dev).manual_seed(0)
+    q, k, v = (torch.randn(1, H, S, D, device=dev, generator=g).to(torch.bfloat16) for _ in range(3))
     from svgb200 import core
 
-    for QC, KC in ((400, 1000), (465, 931)):
-        bm, row, col, fl = varblock_inputs(QC, KC, 0.3)
-        bmd, rd, cd = bm.to(dev), row.to(dev), col.to(dev)
+    # ------------------------------------------------------------------ SVG2: variable-block map, rho = 0.30
+    try:
+        import flashinfer
+
+        out["flashinfer_version"] = getattr(flashinfer, "__version__", "?")
+        bm, row, col, fl = bench.svg2_map(H, seed=7)
+        bmd, rd, cd = bm.to(dev)[None], row.to(dev)[None], col.to(dev)[None]
+        t0 = time.time()
+        o_ref, how = R.reference_flashinfer_varblock(q, k, v, bmd, rd, cd)
+        torch.cuda.synchronize()
+        first = time.time() - t0
+        ms_call = timeit(lambda: R.reference_flashinfer_varblock(q, k, v, bmd, rd, cd), warm=0, iters=3)
+        # run only, on a plan that is kept (the reference re-plans every call)
+        fws = torch.empty(128 * 1024 * 1024, device=dev)
+        w = flashinfer.sparse.VariableBlockSparseAttentionWrapper(fws, backend="auto")
+        w.plan(block_mask_map=bmd[0], block_row_sz=rd[0], block_col_sz=cd[0], num_qo_heads=H, num_kv_heads=H, head_dim=D,
+               q_data_type=q.dtype, kv_data_type=k.dtype)
+        q3, k3, v3 = (t.reshape(H, S, D) for t in (q, k, v))
+        ms_run = timeit(lambda: w.run(q3, k3, v3), warm=1, iters=3)
+        del w, fws
 
         def ours():
-            plan = core.plan_varblock(bmd, rd, cd, S)
-            return core.attn_fwd(q, k, v, plan)
-        ms = timeit(ours)
-        emit(path="ours.varblock(plan+run)", QC=QC, KC=KC, ms=ms, tflops=fl / ms / 1e9)
-except Exception as e:  # noqa: BLE001
-    emit(path="ours.varblock", error=repr(e))
-
-# ------------------------------------------------------------------------------------------ R-FI
-try:
-    import flashinfer
-
-    emit(path="flashinfer", version=getattr(flashinfer, "__version__", "?"))
-    for QC, KC in ((400, 1000), (465, 931)):
-        bm, row, col, fl = varblock_inputs(QC, KC, 0.3)
-        bmd, rd, cd = bm.to(dev), row.to(dev), col.to(dev)
-        float_ws = torch.empty(128 * 1024 * 1024, device=dev)            # kmeans_utils.py:1358
-        vec_idx = torch.empty(1024 * 1024 * 1024, device=dev)             # :1359 (4 GiB fp32 scratch)
-        wrapper = flashinfer.sparse.VariableBlockSparseAttentionWrapper(float_ws, backend="auto")
-        try:  # the reference enlarges the index scratch (kmeans_utils.py:1361-1366); attribute names moved in 0.6.x
-            wrapper.reset_workspace_buffer(float_workspace_buffer=wrapper._float_workspace_buffer,
-                                           int_workspace_buffer=wrapper._int_workspace_buffer,
-                                           vector_sparse_indices_buffer=vec_idx,
-                                           vector_sparse_indptr_buffer=wrapper._vector_sparse_indptr_buffer)
-        except Exception as e:  # noqa: BLE001
-            emit(path="R-FI.note", note="reset_workspace_buffer unavailable in this flashinfer: " + repr(e)[:200])
-        q3, k3, v3 = (t.reshape(H, S, D) for t in (q, k, v))
-
-        def plan():
-            wrapper.plan(block_mask_map=bmd, block_row_sz=rd, block_col_sz=cd, num_qo_heads=H, num_kv_heads=H,
-                         head_dim=D, q_data_type=q.dtype, kv_data_type=k.dtype)
-
-        t0 = time.time()
-        plan()
-        o = wrapper.run(q3, k3, v3)
-        torch.cuda.synchronize()
-        emit(path="R-FI.first_call_s", QC=QC, KC=KC, seconds=time.time() - t0)
-        ms_run = timeit(lambda: wrapper.run(q3, k3, v3), warm=1, iters=3)
-
-        def both():
-            plan()
-            return wrapper.run(q3, k3, v3)
-        ms_both = timeit(both, warm=1, iters=3)
-        emit(path="R-FI.varblock", QC=QC, KC=KC, ms_run=ms_run, ms_plan_run=ms_both, tflops_run=fl / ms_run / 1e9,
-             tflops_plan_run=fl / ms_both / 1e9)
-        try:
-            from svgb200 import core
-            ours_o = core.attn_fwd(q, k, v, core.plan_varblock(bmd, rd, cd, S))
-            diff = (ours_o.view(H, S, D).float() - o.float()).abs().max().item()
-            emit(path="R-FI.vs_ours_max_abs_diff", QC=QC, KC=KC, diff=diff)
-        except Exception as e:  # noqa: BLE001
-            emit(path="R-FI.compare", error=repr(e))
-        del wrapper, float_ws, vec_idx
+            return core.attn_fwd(q, k, v, core.plan_varblock(bmd[0], rd[0], cd[0], S))
+        o_ours = ours()
+        ms_ours = timeit(ours, warm=1, iters=5)
+        out["svg2_varblock"] = {
+            "workload": f"QC=400+2 / KC=1000+2 Bernoulli(0.30) map incl. prompt / padding blocks, {H} heads (bench.svg2_map)",
+            "reference": "svg.kmeans_utils.dynamic_block_sparse_fwd_flashinfer (svg/kmeans_utils.py:1319-1392): " + how,
+            "ref_ms_per_call": ms_call, "ref_ms_run_only": ms_run, "ref_first_call_s": first,
+            "ref_tflops": fl / ms_call / 1e9, "ref_tflops_run_only": fl / ms_run / 1e9,
+            "ours_ms_per_call_plan_plus_run": ms_ours, "ours_tflops": fl / ms_ours / 1e9,
+            "speedup_vs_call": ms_call / ms_ours, "speedup_vs_run_only": ms_run / ms_ours,
+            "max_abs_diff": (o_ours.float() - o_ref.float()).abs().max().item(),
+        }
+        del o_ref, o_ours
         torch.cuda.empty_cache()
-except Exception as e:  # noqa: BLE001
-    emit(path="R-FI", error=repr(e), tb=traceback.format_exc()[-1500:])
-
-# ------------------------------------------------------------------------------------------ R-FX
-try:
-    if os.environ.get("REF_SKIP_FX"):
-        raise RuntimeError("skipped (REF_SKIP_FX)")
-    from torch.nn.attention.flex_attention import create_block_mask, flex_attention
-
-    W, mul = bench.band_width()
-    real_length = F * P + PLEN
-
-    def temporal_mask_mod(b, h, q_idx, kv_idx):   # hyvideo/utils.py:29-42
-        real_mask = (kv_idx < real_length) & (q_idx < real_length)
-        fake_mask = (kv_idx >= real_length) & (q_idx >= real_length)
-        temporal_head_mask = torch.abs(q_idx - kv_idx) < W
-        text_column_mask = (F * P <= kv_idx) & (kv_idx < real_length)
-        text_row_mask = (F * P <= q_idx) & (q_idx < real_length)
-        return (real_mask & (temporal_head_mask | text_column_mask | text_row_mask)) | fake_mask
-
-    t0 = time.time()
-    block_mask = create_block_mask(temporal_mask_mod, None, None, S, S, device=dev, _compile=True)
-    flex = torch.compile(flex_attention, dynamic=False)                  # hyvideo/attention.py:30
-    o = flex(q, k, v, block_mask=block_mask)
-    torch.cuda.synchronize()
-    emit(path="R-FX.compile_s", seconds=time.time() - t0)
-    ms = timeit(lambda: flex(q, k, v, block_mask=block_mask), warm=1, iters=3)
-    fl = 4.0 * D * bench.band_pairs(W) * H
-    emit(path="R-FX.flex_attention_band", W=W, ms=ms, tflops=fl / ms / 1e9)
-    try:
-        from svgb200 import core
-        plan = core.plan_band(core.MASK_HY, F * P, real_length, W, H, S, dev)
-        ours_o = core.attn_fwd(q, k, v, plan)
-        emit(path="R-FX.vs_ours_max_abs_diff", diff=(ours_o.float() - o.float()).abs().max().item())
-        ms_o = timeit(lambda: core.attn_fwd(q, k, v, plan))
-        emit(path="ours.band", ms=ms_o, tflops=fl / ms_o / 1e9, speedup_vs_flex=ms / ms_o)
     except Exception as e:  # noqa: BLE001
-        emit(path="R-FX.compare", error=repr(e))
-except Exception as e:  # noqa: BLE001
-    emit(path="R-FX", error=repr(e), tb=traceback.format_exc()[-1500:])
+        out["svg2_varblock"] = {"error": repr(e)[:300], "tb": traceback.format_exc()[-800:]}
+
+    # ------------------------------------------------------------------ SVG1: band mask, rho = 0.30
+    try:
+        if args.skip_flex:
+            raise RuntimeError("skipped (--skip-flex)")
+        if time.time() - t_start > args.budget_s * 0.5:
+            raise RuntimeError("skipped: time budget used by the FlashInfer section")
+        A = R.import_model_module("hyvideo", "attention")
+        U = R.import_model_module("hyvideo", "utils")
+        W, mul = bench.band_width()
+        t0 = time.time()
+        block_mask = A.prepare_flexattention(1, H, D, torch.bfloat16, dev, CTX, PLEN, F, P, diag_width=mul, multiplier=mul)
+        proc = A.Hunyuan_SVGAttn_Processor2_0(layer_idx=0)
+        o_ref = proc.sparse_flex_attention(q, k, v, block_mask=block_mask)
+        torch.cuda.synchronize()
+        first = time.time() - t0
+        ms_ref = timeit(lambda: proc.sparse_flex_attention(q, k, v, block_mask=block_mask), warm=1, iters=3)
+        fl = 4.0 * D * bench.band_pairs(W) * H
+        plan = core.plan_band(core.MASK_HY, F * P, F * P + PLEN, W, H, S, dev)
+        o_ours = core.attn_fwd(q, k, v, plan)
+        ms_ours = timeit(lambda: core.attn_fwd(q, k, v, plan), warm=1, iters=5)
+        out["svg1_band"] = {
+            "workload": f"HY band mask W={W} (rho 0.295), {H} heads",
+            "reference": "svg.models.hyvideo.attention prepare_flexattention + sparse_flex_attention "
+                         "(torch.compile(flex_attention) + BlockMask; hyvideo/attention.py:30,401-403,527-551), unmodified",
+            "ref_ms_per_call": ms_ref, "ref_compile_s": first, "ref_tflops": fl / ms_ref / 1e9,
+            "ours_ms_per_call": ms_ours, "ours_tflops": fl / ms_ours / 1e9, "speedup": ms_ref / ms_ours,
+            "max_abs_diff": (o_ours.float() - o_ref.float()).abs().max().item(),
+        }
+    except Exception as e:  # noqa: BLE001
+        out["svg1_band"] = {"error": repr(e)[:300], "tb": traceback.format_exc()[-800:]}
+    out["seconds"] = time.time() - t_start
+    print("REF_GPU_JSON " + json.dumps(out), flush=True)
+
+
+if __name__ == "__main__":
+    main()
