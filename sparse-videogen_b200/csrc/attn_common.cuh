@@ -152,6 +152,10 @@ struct MaskRow {
 
 struct AttnArgs {
   const int4* items;
+  // variable-block plans: optional second stream per work item.  items2[i].y > 0 makes item i a DUAL item: two
+  // single-tile streams (<= 128 rows each, usually the tails of two different q-blocks) share one CTA -- T0 runs
+  // items[i], T1 runs items2[i], each with its own chunk list and its own K/V tiles through the common ring.
+  const int4* items2;
   const int* item_count;
   const int2* chunks;
   int items_stride;   // 0: one plan shared by all heads (band masks); else items per head

@@ -15,18 +15,29 @@ namespace svgb {
 // =============================================================================================
 __global__ void plan_varblock_kernel(const uint8_t* __restrict__ map, const int* __restrict__ row_sz,
                                      const int* __restrict__ col_sz, int QC, int KC, int max_items,
-                                     int chunk_cap, int* __restrict__ counts, int4* __restrict__ items,
-                                     int2* __restrict__ chunks, int* __restrict__ item_total) {
+                                     int chunk_cap, int pair_tails, int* __restrict__ counts, int4* __restrict__ items,
+                                     int4* __restrict__ items2, int2* __restrict__ chunks, int* __restrict__ item_total) {
   // item_total != nullptr selects the gather form: the list holds RUNS {start, keys before this run} plus a
   // sentinel {0, total}; the kernel then gathers exactly-full 128-key chunks across run boundaries.
+  //
+  // TMA form (items2 != nullptr): a q-block of r rows becomes r/256 two-tile items (+ one more when r % 256 > 128,
+  // its second tile partial) and, when 0 < r % 256 <= 128, a single-tile TAIL.  Tails are where k-means clusters
+  // lose tensor-core rows (a 297-row cluster = 256 + 41) and single-tile CTAs also run the softmax->MMA loop at
+  // lower throughput, so the tails of a head are sorted by chunk count and packed two per CTA as DUAL items
+  // (items[i] = stream of T0, items2[i] = stream of T1; see AttnArgs::items2).  Launch order: two-tile items in
+  // q-block order, then the dual items from long to short.
   const bool gather = item_total != nullptr;
   extern __shared__ int sm[];
   int* coloff = sm;                 // KC + 1
   int* rowoff = coloff + KC + 1;    // QC + 1
-  int* itembase = rowoff + QC + 1;  // QC + 1
+  int* itembase = rowoff + QC + 1;  // QC + 1 : first two-tile item of the q-block (gather: first item)
+  int* nch_of = itembase + QC + 1;  // QC     : chunk count of the q-block's list
+  int* tail_of = nch_of + QC;       // QC     : rows of the single-tile tail (0 = none)
+  __shared__ int s_total2, s_ntails;
   const int bh = blockIdx.x;
   row_sz += static_cast<size_t>(bh) * QC;
   col_sz += static_cast<size_t>(bh) * KC;
+  const bool pair = !gather && pair_tails;
   if (threadIdx.x == 0) {
     int acc = 0;
     for (int j = 0; j < KC; ++j) {
@@ -36,21 +47,30 @@ __global__ void plan_varblock_kernel(const uint8_t* __restrict__ map, const int*
     coloff[KC] = acc;
   }
   if (threadIdx.x == 32) {
-    int acc = 0, it = 0;
+    int acc = 0, it = 0, nt = 0;
     for (int i = 0; i < QC; ++i) {
       rowoff[i] = acc;
       itembase[i] = it;
       const int r = row_sz[i];
       acc += r;
-      it += (r + kItemRows - 1) / kItemRows;
+      const int rem = r % kItemRows;
+      int tail = 0;
+      if (pair && rem > 0 && rem <= kTileRows) tail = rem;
+      tail_of[i] = tail;
+      nt += tail > 0;
+      it += tail > 0 ? r / kItemRows : (r + kItemRows - 1) / kItemRows;
     }
     rowoff[QC] = acc;
     itembase[QC] = it;
-    counts[bh] = it < max_items ? it : max_items;
+    s_total2 = it;
+    s_ntails = nt;
+    const int total = it + (nt + 1) / 2;
+    counts[bh] = total < max_items ? total : max_items;
   }
   __syncthreads();
   for (int qb = threadIdx.x; qb < QC; qb += blockDim.x) {
     const int r = rowoff[qb + 1] - rowoff[qb];
+    nch_of[qb] = 0;
     if (r == 0) continue;
     const size_t list = (static_cast<size_t>(bh) * QC + qb) * chunk_cap;
     int2* out = chunks + list;
@@ -87,14 +107,40 @@ __global__ void plan_varblock_kernel(const uint8_t* __restrict__ map, const int*
       }
     }
     if (gather) out[n] = make_int2(0, total);  // sentinel: ends the last run
-    const int nit = (r + kItemRows - 1) / kItemRows;
+    nch_of[qb] = n;
+    const int nit = tail_of[qb] > 0 ? r / kItemRows : (r + kItemRows - 1) / kItemRows;
     for (int t = 0; t < nit; ++t) {
       const int idx = itembase[qb] + t;
       if (idx < max_items) {
         items[static_cast<size_t>(bh) * max_items + idx] =
             make_int4(rowoff[qb] + t * kItemRows, min(kItemRows, r - t * kItemRows),
                       static_cast<int>(list), n);
+        if (items2) items2[static_cast<size_t>(bh) * max_items + idx] = make_int4(0, 0, 0, 0);
         if (gather) item_total[static_cast<size_t>(bh) * max_items + idx] = total;
+      }
+    }
+  }
+  if (!pair) return;
+  __syncthreads();
+  // tails: rank by (chunk count descending, q-block ascending); ranks 2i and 2i+1 share dual item i
+  const int ntails = s_ntails, base = s_total2;
+  for (int qb = threadIdx.x; qb < QC; qb += blockDim.x) {
+    const int tail = tail_of[qb];
+    if (tail == 0) continue;
+    const int mine = nch_of[qb];
+    int rank = 0;
+    for (int o = 0; o < QC; ++o)
+      if (tail_of[o] > 0 && (nch_of[o] > mine || (nch_of[o] == mine && o < qb))) ++rank;
+    const int r = rowoff[qb + 1] - rowoff[qb];
+    const int4 it = make_int4(rowoff[qb] + (r / kItemRows) * kItemRows, tail,
+                              static_cast<int>((static_cast<size_t>(bh) * QC + qb) * chunk_cap), mine);
+    const int idx = base + (rank >> 1);
+    if (idx < max_items) {
+      if ((rank & 1) == 0) {
+        items[static_cast<size_t>(bh) * max_items + idx] = it;
+        if (rank == ntails - 1) items2[static_cast<size_t>(bh) * max_items + idx] = make_int4(0, 0, 0, 0);  // odd one out
+      } else {
+        items2[static_cast<size_t>(bh) * max_items + idx] = it;
       }
     }
   }
@@ -330,7 +376,7 @@ static int launch_attn(const CUtensorMap& qm, const CUtensorMap& km, const CUten
   if constexpr (DT != DT_E4M3 && D == 128) {
     // experimental sub-chunk pipeline (attn_kernel.cuh, kSub): opt-in until it is validated on the GPU
     static const int sub = [] { const char* e = getenv("SVGB_ATTN_SUB"); return (e && (e[0] == '1' || e[0] == '2')) ? e[0] - '0' : 0; }();
-    if (sub && !args.softmax_shared) {
+    if (sub && !args.softmax_shared && !args.items2) {
       auto kern = attn_fwd_kernel<D, DT, false, true>;
       SVGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
       AttnArgs sub_args = args;
@@ -397,7 +443,8 @@ int svgb_attn_plan_varblock_bytes(int BH, int S, int QC, int KC, size_t* bytes) 
   const size_t counts = align_up(sizeof(int) * BH, 256);
   const size_t items = align_up(sizeof(int4) * BH * varblock_max_items(S, QC), 256);
   const size_t chunks = align_up(sizeof(int2) * static_cast<size_t>(BH) * QC * varblock_chunk_cap(S, KC), 256);
-  const size_t aux = align_up(sizeof(int) * BH * varblock_max_items(S, QC), 256);  // gather plans: keys per item
+  // aux: TMA plans = second stream of dual items (int4 per item); gather plans = selected keys per item (int)
+  const size_t aux = align_up(sizeof(int4) * BH * varblock_max_items(S, QC), 256);
   *bytes = counts + items + chunks + aux;
   return 0;
 }
@@ -429,12 +476,14 @@ static int plan_varblock_impl(const uint8_t* map, const int32_t* row_sz, const i
   plan->aux_off = plan->chunks_off + align_up(sizeof(int2) * static_cast<size_t>(BH) * QC * cap, 256);
   plan->bytes = need;
   char* ws = static_cast<char*>(plan_ws);
-  const size_t smem = sizeof(int) * (KC + 1 + 2 * (QC + 1));
+  const size_t smem = sizeof(int) * (KC + 1 + 2 * (QC + 1) + 2 * QC);
   SVGB_REQUIRE(smem <= 48 * 1024, "QC/KC too large for the plan kernel (%zu B smem)", smem);
+  // SVGB_ATTN_PAIR=0 keeps every tail a single-tile item (A/B switch for bring-up)
+  static const int pair_tails = [] { const char* e = getenv("SVGB_ATTN_PAIR"); return (e && e[0] == '0') ? 0 : 1; }();
   plan_varblock_kernel<<<BH, 256, smem, static_cast<cudaStream_t>(stream)>>>(
-      map, row_sz, col_sz, QC, KC, max_items, cap, reinterpret_cast<int*>(ws + plan->counts_off),
-      reinterpret_cast<int4*>(ws + plan->items_off), reinterpret_cast<int2*>(ws + plan->chunks_off),
-      gather ? reinterpret_cast<int*>(ws + plan->aux_off) : nullptr);
+      map, row_sz, col_sz, QC, KC, max_items, cap, pair_tails, reinterpret_cast<int*>(ws + plan->counts_off),
+      reinterpret_cast<int4*>(ws + plan->items_off), gather ? nullptr : reinterpret_cast<int4*>(ws + plan->aux_off),
+      reinterpret_cast<int2*>(ws + plan->chunks_off), gather ? reinterpret_cast<int*>(ws + plan->aux_off) : nullptr);
   SVGB_LAUNCH_OK();
   return 0;
 }
@@ -515,6 +564,7 @@ static int attn_fwd_entry(const void* q, const void* k, const void* v, const flo
   a.items = reinterpret_cast<const int4*>(ws + plan->items_off);
   a.item_count = reinterpret_cast<const int*>(ws + plan->counts_off);
   a.chunks = reinterpret_cast<const int2*>(ws + plan->chunks_off);
+  a.items2 = plan->kind == 1 ? reinterpret_cast<const int4*>(ws + plan->aux_off) : nullptr;
   a.items_stride = plan->items_stride;
   a.counts_stride = plan->counts_stride;
   a.o = o;
@@ -530,8 +580,16 @@ static int attn_fwd_entry(const void* q, const void* k, const void* v, const flo
   a.m2 = plan->m2;
   a.q_index = nullptr;
   a.out_f32 = 0;
-  // variable-block plans over small key clusters are made of narrow chunks: latency-bound steps
-  a.softmax_shared = (plan->kind == 1 && plan->m1 > 0 && plan->m1 < 256) ? 1 : 0;
+  // Softmax thread mapping of two-tile (and dual) items: 0 = one warpgroup per tile, 1 = both warpgroups share a tile.
+  // Round 1 chose the shared mapping for plans made of narrow chunks (small key clusters); with the straight-line
+  // masked specialisations (attn_kernel.cuh) the per-tile mapping is as fast there (705 vs 704 TF/s at QC=400/KC=1000)
+  // and 4-5 % faster on aligned plans (1177-1188 vs 1126), so it is used everywhere.  Single-tile items always use the
+  // shared mapping.
+  a.softmax_shared = 0;
+  {  // SVGB_ATTN_MAP=0 / 1 forces the per-tile / shared softmax mapping (A/B switch for bring-up)
+    static const int force = [] { const char* e = getenv("SVGB_ATTN_MAP"); return (e && (e[0] == '0' || e[0] == '1')) ? e[0] - '0' : -1; }();
+    if (force >= 0) a.softmax_shared = force;
+  }
   a.sub_mode = 0;
   a.q_scale = q_scale;
   a.k_scale = k_scale;

@@ -84,6 +84,12 @@ __device__ long long g_attn_trace[3 * 64 * 8];
 #endif
 
 constexpr float kRescaleTau = 8.0f;  // log2 units
+// which of the 16 column pairs of a 32-column group evaluate exp2 by polynomial on the FMA pipe instead of MUFU.EX2.
+// Measured on a B200 (same box, profiles/r02_softmax_variants.jsonl): 1/4 -> 1003-1015 TF/s on the band plan,
+// 3/8 -> 978, 1/2 -> 925-933 (and 12.5 % slower than 1/4 in round 1): every extra polynomial costs ~6 issue slots.
+#ifndef SVGB_POLY_SEL
+#define SVGB_POLY_SEL(i) (((i) & 3) == 3)
+#endif
 // register budget per role (launch: 384 threads x 168): warps 0-3 give registers to the 8 softmax warps
 constexpr int kRegsLight = 56;   // 128 x 56 + 256 x 224 = 64512 = the launch allocation (384 x 168)
 constexpr int kRegsSoftmax = 224;
@@ -103,15 +109,27 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
   const int n_items = args.item_count[bh * args.counts_stride];
   if (static_cast<int>(blockIdx.x) >= n_items) return;
   const int4 item = args.items[static_cast<size_t>(bh) * args.items_stride + blockIdx.x];
+  int4 item2 = make_int4(0, 0, 0, 0);
+  if constexpr (!kGather && !kSub) {
+    if (args.items2) item2 = args.items2[static_cast<size_t>(bh) * args.items_stride + blockIdx.x];
+  }
+  // dual item: T0 and T1 are two independent single-tile streams (own rows, own chunk list, own K/V tiles)
+  const bool dual = item2.y > 0;
   const int q_row0 = item.x, nrows = item.y, chunk0 = item.z;
-  const int ntiles = nrows > kTileRows ? 2 : 1;
+  const int ntiles = (dual || nrows > kTileRows) ? 2 : 1;
   const bool per_tile_map = ntiles == 2 && !args.softmax_shared;  // softmax thread mapping (see below)
   const int2* __restrict__ chunks = args.chunks + chunk0;
+  // per-tile view (a regular two-tile item is the special case "same list, rows 128 apart, K/V shared")
+  const int q0_t0 = item.x, q0_t1 = dual ? item2.x : item.x + kTileRows;
+  const int nr_t0 = dual ? item.y : min(item.y, kTileRows), nr_t1 = dual ? item2.y : item.y - kTileRows;
+  const int2* __restrict__ chunks_t1 = dual ? args.chunks + item2.z : chunks;
+  const int nch_t1 = dual ? item2.w : item.w;
   constexpr bool gather = kGather;
   // gather mode: item.w = number of runs, chunks are implicit (128 selected keys each, last one partial)
   const int nruns = gather ? item.w : 0;
   const int total_kv = gather ? args.item_total[static_cast<size_t>(bh) * args.items_stride + blockIdx.x] : 0;
   const int nchunks = gather ? (total_kv + kChunkCols - 1) / kChunkCols : item.w;
+  const int nch_any = dual ? max(item.w, nch_t1) : nchunks;  // > 0 iff any MMA is issued for this item
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = smem_u32(smem_raw);
@@ -287,8 +305,34 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
       for (int t = 0; t < ntiles; ++t)
         for (int h = 0; h < Cfg::kHalves; ++h)
           tma_load_3d(sQ + t * Cfg::kTileBytes + h * Cfg::kPanelBytes, &qmap, qbar, h * Cfg::kPanelElems,
-                      q_row0 + t * kTileRows, bh);
+                      t == 0 ? q0_t0 : q0_t1, bh);
       int it = 0;
+      if (dual) {
+        // ring order of a dual item (the MMA issuer consumes in exactly this order):
+        //   K0(0) K1(0) | V0(0) K0(1) V1(0) K1(1) | V0(1) K0(2) V1(1) K1(2) | ...   (entries past a stream's end are skipped)
+        auto load = [&](const CUtensorMap* map, int kv0) {
+          const int slot = it % kStages;
+          mbar_wait(smem_u32(&bars->kv_empty[slot]), ((it / kStages) & 1) ^ 1, 1);
+          const uint32_t fb = smem_u32(&bars->kv_full[slot]);
+          mbar_expect_tx(fb, Cfg::kTileBytes);
+          for (int h = 0; h < Cfg::kHalves; ++h)
+            tma_load_3d(sRing + slot * Cfg::kTileBytes + h * Cfg::kPanelBytes, map, fb, h * Cfg::kPanelElems, kv0, bh);
+          ++it;
+        };
+        const int n0 = item.w, n1 = nch_t1, nmax = max(n0, n1);
+        if (n0 > 0) load(&kmap, __ldg(&chunks[0].x));
+        if (n1 > 0) load(&kmap, __ldg(&chunks_t1[0].x));
+        for (int j = 0; j < nmax; ++j) {
+          if (j < n0) {
+            load(&vmap, __ldg(&chunks[j].x));
+            if (j + 1 < n0) load(&kmap, __ldg(&chunks[j + 1].x));
+          }
+          if (j < n1) {
+            load(&vmap, __ldg(&chunks_t1[j].x));
+            if (j + 1 < n1) load(&kmap, __ldg(&chunks_t1[j + 1].x));
+          }
+        }
+      } else
       for (int j = 0; j < nchunks; ++j) {
         const int kv0 = __ldg(&chunks[j].x);
 #pragma unroll
@@ -382,7 +426,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
     } else
     // ---- two-tile items: streamed issue (elect.sync leader, running descriptors), so the tensor pipe runs at its
     // 64 cycles per M=128,N=128,K=16 MMA instead of the ~90 cycles a rebuilt-descriptor loop can issue at
-    if (nchunks > 0 && elect_one()) {  // elect.sync: ptxas then knows a single lane runs the tcgen05 stream
+    if (nch_any > 0 && elect_one()) {  // elect.sync: ptxas then knows a single lane runs the tcgen05 stream
       // MMA N of chunk jj: run-tail / band chunks carry it in the chunk list; gather chunks are all full
       // except the last
       auto chunk_n = [&](int jj) -> int {
@@ -439,6 +483,67 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
           }
         }
       };
+      if (dual) {
+        // ---- dual item: two independent single-tile streams.  Same interleaving as the shared-K/V loop below
+        // (PV_t(j), QK_t(j+1) per tile, tiles alternating) but every stream has its own ring entries, in the order
+        // the producer loads them; a stream that ends early simply drops out.
+        auto chunk_n_t = [&](int t, int jj) -> int {
+          const int vld = chunk_valid(__ldg(t == 0 ? &chunks[jj].y : &chunks_t1[jj].y));
+          return (vld + Cfg::kMmaK - 1) & ~(Cfg::kMmaK - 1);
+        };
+        const int n0 = item.w, n1 = nch_t1, nmax = max(n0, n1);
+        mbar_wait(smem_u32(&bars->q_full), 0, 2);
+        int ring = 0;
+        int n_cur0 = n0 > 0 ? chunk_n_t(0, 0) : 0, n_cur1 = n1 > 0 ? chunk_n_t(1, 0) : 0;
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          if ((t == 0 ? n0 : n1) > 0) {
+            const int slot = ring % kStages;
+            mbar_wait(smem_u32(&bars->kv_full[slot]), (ring / kStages) & 1, 3);
+            ++ring;
+            tc_fence_after();
+            issue_qk(t, k_lo0 + slot * kSlotStep, qk_idesc(t == 0 ? n_cur0 : n_cur1));
+            tc_commit(smem_u32(&bars->s_full[t]));
+            tc_commit(smem_u32(&bars->kv_empty[slot]));
+          }
+        }
+        for (int j = 0; j < nmax; ++j) {
+#pragma unroll
+          for (int t = 0; t < 2; ++t) {
+            const int nt = t == 0 ? n0 : n1;
+            if (j >= nt) continue;
+            const bool has_next = (j + 1 < nt);
+            const int vslot = ring % kStages;
+            const uint32_t vph = (ring / kStages) & 1;
+            ++ring;
+            int kslot = 0, n_next = 0;
+            uint32_t kph = 0;
+            if (has_next) {
+              kslot = ring % kStages;
+              kph = (ring / kStages) & 1;
+              ++ring;
+              n_next = chunk_n_t(t, j + 1);
+            }
+            const uint32_t v_lo = v_lo0 + vslot * kSlotStep, k_lo = k_lo0 + kslot * kSlotStep;
+            const uint32_t idesc_next = qk_idesc(n_next);
+            mbar_wait(smem_u32(&bars->kv_full[vslot]), vph, 4);
+            mbar_wait(smem_u32(&bars->p_full[t]), j & 1, 5 + 2 * t);
+            tc_fence_after();
+            issue_pv(t, v_lo, t == 0 ? n_cur0 : n_cur1, j > 0);
+            tc_commit(smem_u32(&bars->kv_empty[vslot]));
+            if (has_next) {
+              mbar_wait(smem_u32(&bars->kv_full[kslot]), kph, 6);
+              tc_fence_after();
+              issue_qk(t, k_lo, idesc_next);
+              tc_commit(smem_u32(&bars->s_full[t]));
+              tc_commit(smem_u32(&bars->kv_empty[kslot]));
+            }
+            if (t == 0) n_cur0 = n_next;
+            else n_cur1 = n_next;
+          }
+        }
+        tc_commit(smem_u32(&bars->o_final));
+      } else
       if constexpr (kSub) {
         // ---- sub-chunk pipeline (experimental, SVGB_ATTN_SUB=1): every 128-key chunk is two 64-key halves with
         // their own S sub-buffer (S_t columns [64h, 64h+64), P over the first 32 of them).  QK_t,h(j+1) follows
@@ -478,46 +583,70 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
           }
         };
         mbar_wait(smem_u32(&bars->q_full), 0, 2);
-        int n_cur = chunk_n(0);
         mbar_wait(smem_u32(&bars->kv_full[0]), 0, 3);
         tc_fence_after();
-        for (int h = 0; h < 2; ++h)
-          for (int t = 0; t < 2; ++t) {
-            issue_qk_h(t, h, k_lo0, half_cols(n_cur, h));
-            tc_commit(smem_u32(&bars->sub_s[t][h]));
-          }
-        tc_commit(smem_u32(&bars->kv_empty[0]));
-        int ring = 1;
-        for (int j = 0; j < nchunks; ++j) {
-          const bool has_next = (j + 1 < nchunks);
-          const int vslot = ring % kStages;
-          const uint32_t vph = (ring / kStages) & 1;
-          ++ring;
-          int kslot = 0, n_next = 0;
-          uint32_t kph = 0;
-          if (has_next) {
-            kslot = ring % kStages;
-            kph = (ring / kStages) & 1;
-            ++ring;
-            n_next = chunk_n(j + 1);
-          }
-          const uint32_t v_lo = v_lo0 + vslot * kSlotStep, k_lo = k_lo0 + kslot * kSlotStep;
-          mbar_wait(smem_u32(&bars->kv_full[vslot]), vph, 4);
-          if (has_next) mbar_wait(smem_u32(&bars->kv_full[kslot]), kph, 6);
+        {
+          const int n0c = chunk_n(0);
           for (int h = 0; h < 2; ++h)
             for (int t = 0; t < 2; ++t) {
-              mbar_wait(smem_u32(&bars->sub_p[t][h]), j & 1, 5 + t);
-              tc_fence_after();
-              issue_pv_h(t, h, v_lo, half_cols(n_cur, h), j > 0 || h > 0);
-              tc_commit(smem_u32(&bars->sub_pv[t]));
-              if (has_next) {
-                issue_qk_h(t, h, k_lo, half_cols(n_next, h));
-                tc_commit(smem_u32(&bars->sub_s[t][h]));
-              }
+              issue_qk_h(t, h, k_lo0, half_cols(n0c, h));
+              tc_commit(smem_u32(&bars->sub_s[t][h]));
             }
-          tc_commit(smem_u32(&bars->kv_empty[vslot]));
-          if (has_next) tc_commit(smem_u32(&bars->kv_empty[kslot]));
-          n_cur = n_next;
+        }
+        tc_commit(smem_u32(&bars->kv_empty[0]));
+        // ---- ARRIVAL-ORDER service.  Every (tile, half) sub-step of chunk j is served as soon as its P half is
+        // written: PV_t,h(j) then QK_t,h(j+1).  The two tiles are served in whatever order their softmax warpgroups
+        // arrive (a fixed T0,T1 order makes the issuer sit on the slower tile's barrier while the other one's P is
+        // ready, which locks the two warpgroups into the same phase: both in their MUFU-bound exp section at once,
+        // the tensor pipe fed in bursts).  Ring entries: K(0) = 0, V(j) = 2j+1, K(j+1) = 2j+2; V(j) and K(j+1) are
+        // released when BOTH tiles have served (j, half 1).
+        int jt0 = 0, jt1 = 0, ht0 = 0, ht1 = 0;  // next sub-step of each tile
+        int last_full0 = -1, last_full1 = -1;    // last chunk whose half 1 the tile has served
+        auto bar_ready = [](uint32_t bar, uint32_t parity) -> bool {
+          uint32_t ok;
+          asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                       : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+          return ok != 0;
+        };
+        while (jt0 < nchunks || jt1 < nchunks) {
+#pragma unroll
+          for (int t = 0; t < 2; ++t) {
+            const int j = t == 0 ? jt0 : jt1, h = t == 0 ? ht0 : ht1;
+            if (j >= nchunks) continue;
+            const bool has_next = j + 1 < nchunks;
+            const int ve = 2 * j + 1, ke = 2 * j + 2;
+            const int vslot = ve % kStages, kslot = ke % kStages;
+            if (!bar_ready(smem_u32(&bars->sub_p[t][h]), j & 1)) continue;
+            if (!bar_ready(smem_u32(&bars->kv_full[vslot]), (ve / kStages) & 1)) continue;
+            if (has_next && !bar_ready(smem_u32(&bars->kv_full[kslot]), (ke / kStages) & 1)) continue;
+            tc_fence_after();
+#ifdef SVGB_ATTN_TRACE
+            const int svc = (jt0 * 2 + ht0) + (jt1 * 2 + ht1);  // services done so far
+            if (trace_on && svc < 64) g_attn_trace[(2 * 64 + svc) * 8 + 0] = clock64(), g_attn_trace[(2 * 64 + svc) * 8 + 3] = t * 2 + h;
+#endif
+            const int n_c = chunk_n(j);
+            issue_pv_h(t, h, v_lo0 + vslot * kSlotStep, half_cols(n_c, h), j > 0 || h > 0);
+            tc_commit(smem_u32(&bars->sub_pv[t]));
+            if (has_next) {
+              issue_qk_h(t, h, k_lo0 + kslot * kSlotStep, half_cols(chunk_n(j + 1), h));
+              tc_commit(smem_u32(&bars->sub_s[t][h]));
+            }
+#ifdef SVGB_ATTN_TRACE
+            if (trace_on && svc < 64) g_attn_trace[(2 * 64 + svc) * 8 + 1] = clock64();
+#endif
+            if (h == 1) {
+              const int other = t == 0 ? last_full1 : last_full0;
+              if (other >= j) {  // the other tile is already past this chunk: its K/V tiles are free
+                tc_commit(smem_u32(&bars->kv_empty[vslot]));
+                if (has_next) tc_commit(smem_u32(&bars->kv_empty[kslot]));
+              }
+              if (t == 0) { last_full0 = j; ++jt0; ht0 = 0; }
+              else { last_full1 = j; ++jt1; ht1 = 0; }
+            } else {
+              if (t == 0) ht0 = 1;
+              else ht1 = 1;
+            }
+          }
         }
         tc_commit(smem_u32(&bars->o_final));
       } else {
@@ -610,7 +739,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
     if (t < ntiles) {
       const int wq = warp & 3;
       const int row = wq * 32 + lane;  // row inside the 128-row tile == TMEM lane
-      const int q = q_row0 + t * kTileRows + row;
+      const int q = (t == 0 ? q0_t0 : q0_t1) + row;
+      // this tile's chunk stream (dual items: its own list; otherwise the item's)
+      const int2* __restrict__ my_chunks = t == 0 ? chunks : chunks_t1;
+      const int my_n = dual ? (t == 0 ? item.w : nch_t1) : nchunks;
       const int qm = (args.q_index && q < args.S) ? __ldg(&args.q_index[q]) : q;  // position seen by the mask
       const uint32_t lane_addr = tmem + (static_cast<uint32_t>(wq * 32) << 16);
       const uint32_t s_addr = lane_addr + (t == 0 ? Cfg::kSCol0 : Cfg::kSCol1);
@@ -626,7 +758,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
 
       float m_used = -INFINITY;  // reference max the stored P / O are scaled against
       float l_run = 0.f;
-      int2 ch = (nchunks > 0 && !gather) ? __ldg(&chunks[0]) : make_int2(0, 0);
+      int2 ch = (my_n > 0 && !gather) ? __ldg(&my_chunks[0]) : make_int2(0, 0);
       MaskRow mrow;
       mrow.init(mode, qm, m0, m1, m2);
 
@@ -657,8 +789,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
           const int nh = min(max(ncols - 64 * h, 0), 64);  // MMA columns of this half
           const int vh = min(max(valid - 64 * h, 0), 64);  // valid key columns of this half
           const uint32_t sh_addr = s_addr + 64 * h;
+          SVGB_TRACE(t, nsub, 0);
           mbar_wait(smem_u32(&bars->sub_s[t][h]), j & 1, 8 + t);
           tc_fence_after();
+          SVGB_TRACE(t, nsub, 1);
           if (nh > 0) {
             float rs;
             auto half_body = [&](auto plain_tag) {
@@ -667,6 +801,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
               tmem_ld32(sh_addr, r0);
               if (kPlain || nh > 32) tmem_ld32(sh_addr + 32, r1);
               tc_wait_ld();
+              SVGB_TRACE(t, nsub, 2);
               if constexpr (!kPlain) {
                 auto sanitize = [&](uint32_t(&rr)[32], int gl) {
                   const int left = vh - gl * 32;
@@ -692,6 +827,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
                 alpha = ex2_approx((m_used - m_new) * c);
                 m_used = m_new;
               }
+              SVGB_TRACE(t, nsub, 3);
               flush_pending();  // P of the previous sub-step: its stores landed while this one loaded and reduced
               if (nsub > 0 && __any_sync(0xffffffffu, alpha != 1.f)) {
                 // every PV group issued so far must have landed in O_t before it is rescaled
@@ -721,7 +857,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
                   const uint64_t x2 =
                       ffma2(pack_f32x2(__uint_as_float(rr[2 * i]), __uint_as_float(rr[2 * i + 1])), c2, nmc2);
                   float p0, p1;
-                  if ((i & 3) == 3) {
+                  if (SVGB_POLY_SEL(i)) {
                     ex2_poly2(x2, p0, p1);
                   } else {
                     float x0, x1;
@@ -730,12 +866,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
                     p1 = ex2_approx(x1);
                   }
                   sum2 = fadd2(sum2, pack_f32x2(p0, p1));
-                  pk[i] = pack2<BF16>(p0, p1);
+                  pk[i] = pack2_p<BF16>(p0, p1);
                 }
                 tmem_st16(sh_addr + gl * 16, pk);
               };
               group_p(r0, 0);
               group_p(r1, 1);
+              SVGB_TRACE(t, nsub, 4);
               float s0, s1;
               unpack_f32x2(sum2, s0, s1);
               rs = s0 + s1;
@@ -744,6 +881,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
             else half_body(std::false_type{});
             l_run += rs;
             if (!defer) tc_wait_st();
+            SVGB_TRACE(t, nsub, 5);
           }
           if (defer) {
             flush_pending();  // only still pending when this half was empty (nh == 0)
@@ -752,18 +890,19 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
           } else {
             tc_fence_before();
             mbar_arrive(smem_u32(&bars->sub_p[t][h]));
+            SVGB_TRACE(t, nsub, 6);
           }
         }
       }
       flush_pending();
       } else
-      for (int j = 0; j < nchunks; ++j) {
+      for (int j = 0; j < my_n; ++j) {
         const int kv0 = ch.x;
         const int valid = gather ? min(kChunkCols, total_kv - j * kChunkCols) : chunk_valid(ch.y);
         const bool elem = !gather && (ch.y & kChunkElem) != 0;
         const int ncols = (valid + Cfg::kMmaK - 1) & ~(Cfg::kMmaK - 1);
         const int ngroups = (ncols + 31) >> 5;
-        if (!gather && j + 1 < nchunks) ch = __ldg(&chunks[j + 1]);
+        if (!gather && j + 1 < my_n) ch = __ldg(&my_chunks[j + 1]);
 
         SVGB_TRACE(t, j, 0);
         mbar_wait(sbar, j & 1, 8 + t);
@@ -775,39 +914,47 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
         // the general form, which first overwrites disallowed scores with -inf in place (run tails,
         // band edges, profiling masks) -- exp2(-inf) = 0 then makes the rest identical to the plain path.
         float rs;
-        auto chunk_body = [&](auto plain_tag) {
+        // Three straight-line specialisations (no per-group run-time guards, static register allocation):
+        //   plain   : full unmasked 128-column chunk
+        //   masked<4>: any other chunk wider than 64 columns -- all four 32-column groups are processed; columns past
+        //             `valid` (stale TMEM contents when the MMA N was < 128) and element-masked ones become -inf
+        //   masked<2>: chunks of at most 64 columns -- two groups
+        auto chunk_body = [&](auto plain_tag, auto groups_tag) {
           constexpr bool kPlain = decltype(plain_tag)::value;
-          uint32_t r0[32], r1[32], r2[32], r3[32];
+          constexpr int kG = decltype(groups_tag)::value;
+          uint32_t r0[32], r1[32], r2[kG == 4 ? 32 : 1], r3[kG == 4 ? 32 : 1];
           tmem_ld32(s_addr, r0);
-          if (kPlain || ngroups > 1) tmem_ld32(s_addr + 32, r1);
-          if (kPlain || ngroups > 2) tmem_ld32(s_addr + 64, r2);
-          if (kPlain || ngroups > 3) tmem_ld32(s_addr + 96, r3);
+          tmem_ld32(s_addr + 32, r1);
+          if constexpr (kG == 4) {
+            tmem_ld32(s_addr + 64, r2);
+            tmem_ld32(s_addr + 96, r3);
+          }
           tc_wait_ld();
           SVGB_TRACE(t, j, 2);
           if constexpr (!kPlain) {
             auto sanitize = [&](uint32_t(&rr)[32], int g) {
               const int left = valid - g * 32;
-              if (g >= ngroups || !(elem || left < 32)) return;  // warp-uniform
-              uint32_t bits = left >= 32 ? 0xffffffffu : (1u << left) - 1u;
-              if (elem) bits &= mrow.bits32(kv0 + g * 32);
+              if (!(elem || left < 32)) return;  // warp-uniform
+              uint32_t bits = left >= 32 ? 0xffffffffu : (left > 0 ? (1u << left) - 1u : 0u);
+              if (elem && left > 0) bits &= mrow.bits32(kv0 + g * 32);
 #pragma unroll
               for (int i = 0; i < 32; ++i) rr[i] = (bits >> i) & 1u ? rr[i] : 0xff800000u;  // -inf
             };
             sanitize(r0, 0);
             sanitize(r1, 1);
-            sanitize(r2, 2);
-            sanitize(r3, 3);
-          }
-          auto group_max = [&](const uint32_t(&rr)[32], int g) -> float {
-            float m = -INFINITY;
-            if constexpr (!kPlain) {
-              if (g >= ngroups) return m;
+            if constexpr (kG == 4) {
+              sanitize(r2, 2);
+              sanitize(r3, 3);
             }
+          }
+          auto group_max = [&](const uint32_t(&rr)[32]) -> float {
+            float m = -INFINITY;
 #pragma unroll
             for (int i = 0; i < 32; ++i) m = fmaxf(m, __uint_as_float(rr[i]));
             return m;
           };
-          const float mx = fmaxf(fmaxf(group_max(r0, 0), group_max(r1, 1)), fmaxf(group_max(r2, 2), group_max(r3, 3)));
+          float mx = fmaxf(group_max(r0), group_max(r1));
+          if constexpr (kG == 4) mx = fmaxf(mx, fmaxf(group_max(r2), group_max(r3)));
           const float m_new = fmaxf(m_used, mx);
           // lazy rescale: keep the stale reference max unless it grew by more than tau (log2 units)
           float alpha = 1.f;
@@ -835,9 +982,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
           // P = exp2(S*c - m*c) -> 16-bit, packed two per TMEM column over the first half of the S tile.
           // Every 4th pair is evaluated on the FMA pipe (polynomial) to unload the MUFU.
           auto group_p = [&](const uint32_t(&rr)[32], int g) {
-            if constexpr (!kPlain) {
-              if (g >= ngroups) return;
-            }
             uint32_t pk[16];
             float rs_hi[FP8 ? 16 : 1];
 #pragma unroll
@@ -845,7 +989,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
               const uint64_t x2 =
                   ffma2(pack_f32x2(__uint_as_float(rr[2 * i]), __uint_as_float(rr[2 * i + 1])), c2, nmc2);
               float p0, p1;
-              if ((i & 3) == 3) {
+              if (SVGB_POLY_SEL(i)) {
                 ex2_poly2(x2, p0, p1);
               } else {
                 float x0, x1;
@@ -858,7 +1002,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
                 pk[i] = __float_as_uint(p0);
                 rs_hi[i] = p1;
               } else {
-                pk[i] = pack2<BF16>(p0, p1);
+                pk[i] = pack2_p<BF16>(p0, p1);
               }
             }
             if constexpr (FP8) {
@@ -873,15 +1017,18 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
           };
           group_p(r0, 0);
           group_p(r1, 1);
-          group_p(r2, 2);
-          group_p(r3, 3);
+          if constexpr (kG == 4) {
+            group_p(r2, 2);
+            group_p(r3, 3);
+          }
           SVGB_TRACE(t, j, 4);
           float s0, s1;
           unpack_f32x2(sum2, s0, s1);
           rs = s0 + s1;
         };
-        if (!elem && valid == kChunkCols) chunk_body(std::true_type{});
-        else chunk_body(std::false_type{});
+        if (!elem && valid == kChunkCols) chunk_body(std::true_type{}, std::integral_constant<int, 4>{});
+        else if (ngroups <= 2) chunk_body(std::false_type{}, std::integral_constant<int, 2>{});
+        else chunk_body(std::false_type{}, std::integral_constant<int, 4>{});
         l_run += rs;
         tc_wait_st();
         SVGB_TRACE(t, j, 5);
@@ -891,8 +1038,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
       }
 
       // ---------------- epilogue: O / l -> 16-bit -> global (optionally scattered rows)
-      const bool row_ok = (t * kTileRows + row) < nrows;
-      if (nchunks > 0) {
+      const bool row_ok = row < (t == 0 ? nr_t0 : nr_t1);
+      if (nch_any > 0) {
         mbar_wait(smem_u32(&bars->o_final), 0, 10 + t);
         tc_fence_after();
       }
@@ -905,7 +1052,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
 #pragma unroll 1
       for (int g = 0; g < D / 32; ++g) {
         uint32_t o[32];
-        if (nchunks > 0) {
+        if (my_n > 0) {
           tmem_ld32(o_addr + g * 32, o);
           tc_wait_ld();
         } else {
@@ -970,24 +1117,25 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
 
       float m_used[2] = {-INFINITY, -INFINITY};  // per tile: reference max the stored P / O are scaled against
       float l_run[2] = {0.f, 0.f};               // per tile: this thread's half of the row sum
-      int2 ch = (nchunks > 0 && !gather) ? __ldg(&chunks[0]) : make_int2(0, 0);
+      const int n_t0 = dual ? item.w : nchunks, n_t1 = dual ? nch_t1 : nchunks;  // chunk count of each tile's stream
 
-      for (int j = 0; j < nchunks; ++j) {
-        const int kv0 = ch.x;
-        const int valid = gather ? min(kChunkCols, total_kv - j * kChunkCols) : chunk_valid(ch.y);
-        const bool elem = !gather && (ch.y & kChunkElem) != 0;
-        const int ncols = (valid + Cfg::kMmaK - 1) & ~(Cfg::kMmaK - 1);
-        if (!gather && j + 1 < nchunks) ch = __ldg(&chunks[j + 1]);
-        const int c0 = half * 64;            // first key column of this thread's half
-        const int mycols = ncols - c0;       // <= 0: nothing in this half (narrow chunk)
-
-#pragma unroll 1
-        for (int t = 0; t < ntiles; ++t) {
+      for (int j = 0; j < nch_any; ++j) {
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {  // unrolled: m_used / l_run stay in registers
+          if (t >= ntiles || j >= (t == 0 ? n_t0 : n_t1)) continue;  // dual items: the shorter stream has ended
+          // chunk j of this tile's stream (L1-resident list; both tiles of a regular item read the same entry)
+          const int2 ch = gather ? make_int2(0, 0) : __ldg(t == 0 ? &chunks[j] : &chunks_t1[j]);
+          const int kv0 = ch.x;
+          const int valid = gather ? min(kChunkCols, total_kv - j * kChunkCols) : chunk_valid(ch.y);
+          const bool elem = !gather && (ch.y & kChunkElem) != 0;
+          const int ncols = (valid + Cfg::kMmaK - 1) & ~(Cfg::kMmaK - 1);
+          const int c0 = half * 64;            // first key column of this thread's half
+          const int mycols = ncols - c0;       // <= 0: nothing in this half (narrow chunk)
           // single-tile items ping-pong the two S buffers over the chunk stream (see the MMA issuer)
           const int sb = ntiles == 1 ? (j & 1) : t;
           const uint32_t s_addr = lane_addr + (sb == 0 ? Cfg::kSCol0 : Cfg::kSCol1);
           const uint32_t o_addr = lane_addr + (t == 0 ? Cfg::kOCol0 : Cfg::kOCol1);
-          const int q = q_row0 + t * kTileRows + row;
+          const int q = (t == 0 ? q0_t0 : q0_t1) + row;
 #ifdef SVGB_ATTN_TRACE
           const int tj = ntiles == 1 ? j : 2 * j + t;  // trace slot: (chunk, tile) steps in execution order
 #endif
@@ -1000,14 +1148,17 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
           auto chunk_body = [&](auto plain_tag) {
             constexpr bool kPlain = decltype(plain_tag)::value;
             uint32_t ra[32], rb[32];  // columns [c0, c0+32) and [c0+32, c0+64)
-            if (kPlain || mycols > 0) tmem_ld32(s_addr + c0, ra);
-            if (kPlain || mycols > 32) tmem_ld32(s_addr + c0 + 32, rb);
+            const bool live = kPlain || mycols > 0;  // general form: a half with columns processes both groups
+            if (live) {
+              tmem_ld32(s_addr + c0, ra);
+              tmem_ld32(s_addr + c0 + 32, rb);
+            }
             tc_wait_ld();
             SVGB_TRACE(half, tj, 2);
             if constexpr (!kPlain) {
               auto sanitize = [&](uint32_t(&rr)[32], int g) {  // g: global 32-column group index (0..3)
                 const int left = valid - g * 32;
-                if (g * 32 >= ncols || !(elem || left < 32)) return;  // warp-uniform
+                if (!live || !(elem || left < 32)) return;  // warp-uniform
                 uint32_t bits = left >= 32 ? 0xffffffffu : (left > 0 ? (1u << left) - 1u : 0u);
                 if (elem && left > 0) {
                   const int qm = (args.q_index && q < args.S) ? __ldg(&args.q_index[q]) : q;
@@ -1022,13 +1173,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
               sanitize(rb, 2 * half + 1);
             }
             float mx = -INFINITY;
-            if (kPlain || mycols > 0) {
+            if (live) {
 #pragma unroll
-              for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(ra[i]));
-            }
-            if (kPlain || mycols > 32) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(rb[i]));
+              for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fmaxf(__uint_as_float(ra[i]), __uint_as_float(rb[i])));
             }
             const float m_new = fmaxf(m_used[t], fmaxf(mx, exchange(mx)));
             SVGB_TRACE(half, tj, 3);
@@ -1062,9 +1209,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
             // P = exp2(S*c - m*c) -> 16-bit (or e4m3), packed over the first half of the S tile.  Every 4th
             // pair is evaluated on the FMA pipe (polynomial) to unload the MUFU.
             auto group_p = [&](const uint32_t(&rr)[32], int g) {  // g: global group index
-              if constexpr (!kPlain) {
-                if (g * 32 >= ncols) return;
-              }
+              if (!live) return;
               uint32_t pk[16];
               float rs_hi[FP8 ? 16 : 1];
 #pragma unroll
@@ -1072,7 +1217,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
                 const uint64_t x2 =
                     ffma2(pack_f32x2(__uint_as_float(rr[2 * i]), __uint_as_float(rr[2 * i + 1])), c2, nmc2);
                 float p0, p1;
-                if ((i & 3) == 3) {
+                if (SVGB_POLY_SEL(i)) {
                   ex2_poly2(x2, p0, p1);
                 } else {
                   float x0, x1;
@@ -1085,7 +1230,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
                   pk[i] = __float_as_uint(p0);
                   rs_hi[i] = p1;
                 } else {
-                  pk[i] = pack2<BF16>(p0, p1);
+                  pk[i] = pack2_p<BF16>(p0, p1);
                 }
               }
               if constexpr (FP8) {
@@ -1120,15 +1265,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
 
       // ---------------- epilogue: O / l -> 16-bit -> global (optionally scattered rows); each thread stores its
       // half of the D output columns of both tiles' rows
-      if (nchunks > 0) {
+      if (nch_any > 0) {
         mbar_wait(smem_u32(&bars->o_final), 0, 10);
         tc_fence_after();
       }
 #pragma unroll 1
       for (int t = 0; t < ntiles; ++t) {
         const uint32_t o_addr = lane_addr + (t == 0 ? Cfg::kOCol0 : Cfg::kOCol1);
-        const int q = q_row0 + t * kTileRows + row;
-        const bool row_ok = (t * kTileRows + row) < nrows;
+        const int q = (t == 0 ? q0_t0 : q0_t1) + row;
+        const bool row_ok = row < (t == 0 ? nr_t0 : nr_t1);
+        const bool tile_has_o = (t == 0 ? n_t0 : n_t1) > 0;
         const float l_tot = l_run[t] + exchange(l_run[t]);
         const float inv_l = (l_tot > 0.f ? 1.f / l_tot : 0.f) * (args.v_scale ? __ldg(&args.v_scale[bh]) : 1.f);
         long long out_row = q;
@@ -1140,7 +1286,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
 #pragma unroll 1
         for (int g = 0; g < D / 64; ++g) {
           uint32_t o[32];
-          if (nchunks > 0) {
+          if (tile_has_o) {
             tmem_ld32(o_addr + col0 + g * 32, o);
             tc_wait_ld();
           } else {

@@ -359,4 +359,18 @@ __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
   return r;
 }
 
+// P packing of the softmax inner loop (128 values per row step): cvt.rn.bf16x2.f32 (F2FP.BF16.PACK_AB).
+// -DSVGB_PACK_INT builds the integer form instead (bf16 = upper half of the fp32 word: add half an ulp, pick the two
+// upper halves with one PRMT).  Measured on a B200 (profiles/r02_softmax_variants.jsonl): slower -- 990 vs 1003-1015
+// TF/s on the band plan, 654 vs 699 on the narrow variable-block plan: the softmax step is bound by issue slots /
+// dependent-issue latency of its ~540 instructions per warp, not by the XU pipe, so 3 ALU instructions for 1 F2FP lose.
+template <bool kBF16>
+__device__ __forceinline__ uint32_t pack2_p(float lo, float hi) {
+#ifdef SVGB_PACK_INT
+  if constexpr (kBF16)
+    return __byte_perm(__float_as_uint(lo) + 0x8000u, __float_as_uint(hi) + 0x8000u, 0x7632);
+#endif
+  return pack2<kBF16>(lo, hi);
+}
+
 }  // namespace svgb

@@ -17,8 +17,16 @@ def checksum(*ts):
 
 
 def kmeans_inputs(seed, B, N, D, K, clustered=True):
-    """x bf16 [B,N,D] (mixture of K/4 well-separated blobs + noise when `clustered`), init centroids = rows of x."""
+    """x bf16 [B,N,D] (mixture of K/4 well-separated blobs + noise when `clustered`), init centroids = rows of x.
+    clustered == 2: exactly K well-separated blobs, init = blob centres + small noise (a well-conditioned Lloyd run:
+    every point keeps a large margin, so two correct implementations must agree on the labels, not just on inertia)."""
     g = torch.Generator().manual_seed(int(seed))
+    if int(clustered) == 2:
+        centers = torch.randn(B, K, D, generator=g) * 2.0
+        which = torch.randint(0, K, (B, N), generator=g)
+        x = (torch.gather(centers, 1, which[..., None].expand(-1, -1, D)) + 0.5 * torch.randn(B, N, D, generator=g)).bfloat16()
+        init = (centers + 0.3 * torch.randn(B, K, D, generator=g)).bfloat16()
+        return x, init
     if clustered:
         nb = max(2, K // 4)
         centers = torch.randn(B, nb, D, generator=g) * 2.0

@@ -45,7 +45,7 @@ def main():
     # name: (seed, B, N, D, K, clustered)
     cases = {"small": (21, 2, 6000, 64, 50, True), "mid": (22, 2, 5000, 128, 300, True),
              "hyq": (23, 1, 118800, 128, 400, True), "hyk": (24, 1, 118800, 128, 1000, True),
-             "wank": (25, 1, 75600, 128, 1000, False)}
+             "wank": (25, 1, 75600, 128, 1000, False), "sep": (26, 2, 8000, 64, 40, 2)}
     for name, (seed, B, N, D, K, clustered) in cases.items():
         t0 = time.time()
         x, init = kmeans_inputs(seed, B, N, D, K, clustered)

@@ -24,6 +24,10 @@ for step in "$@"; do
     stages)     timeout 900 python tools/stage_probe.py > gpurun_out/stages.log 2>&1 ;;
     bench)      timeout 900 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err ;;
     bench_ref)  timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err ;;
+    trace)      L=$PWD/sparse-videogen_b200/svgb200/_lib
+                for c in vb band; do for i in 0 1; do
+                  [ -f $L/libsvgb200_trace$i.so ] && SVGB200_LIB=$L/libsvgb200_trace$i.so TRACE_CASE=$c TRACE_TAG=item$i timeout 200 python tools/attn_trace.py >> gpurun_out/trace.log 2>&1
+                done; done ;;
     smoke)      timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1 ;;
     launches)   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 1 > gpurun_out/launches_bench.log 2>&1 ;;
     ncu_band)   PROFILE_MODE=band PROFILE_H=6 timeout 900 ncu --set full --clock-control none --import-source on -k regex:attn_fwd -c 1 -o gpurun_out/attn_band python tools/profile_attn.py > gpurun_out/ncu_band.log 2>&1 ;;
