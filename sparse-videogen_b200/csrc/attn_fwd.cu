@@ -13,69 +13,46 @@ namespace svgb {
 //   one CTA per head; thread per q-block walks its map row, merges selected k-blocks that are
 //   adjacent in token space into runs and cuts runs into <=128-column chunks.
 // =============================================================================================
-__global__ void plan_varblock_kernel(const uint8_t* __restrict__ map, const int* __restrict__ row_sz,
-                                     const int* __restrict__ col_sz, int QC, int KC, int max_items,
-                                     int chunk_cap, int pair_tails, int* __restrict__ counts, int4* __restrict__ items,
-                                     int4* __restrict__ items2, int2* __restrict__ chunks, int* __restrict__ item_total) {
-  // item_total != nullptr selects the gather form: the list holds RUNS {start, keys before this run} plus a
-  // sentinel {0, total}; the kernel then gathers exactly-full 128-key chunks across run boundaries.
-  //
-  // TMA form (items2 != nullptr): a q-block of r rows becomes r/256 two-tile items (+ one more when r % 256 > 128,
-  // its second tile partial) and, when 0 < r % 256 <= 128, a single-tile TAIL.  Tails are where k-means clusters
-  // lose tensor-core rows (a 297-row cluster = 256 + 41) and single-tile CTAs also run the softmax->MMA loop at
-  // lower throughput, so the tails of a head are sorted by chunk count and packed two per CTA as DUAL items
-  // (items[i] = stream of T0, items2[i] = stream of T1; see AttnArgs::items2).  Launch order: two-tile items in
-  // q-block order, then the dual items from long to short.
-  const bool gather = item_total != nullptr;
+// Two kernels.  (1) plan_lists_kernel -- grid (ceil(QC/64), BH): thread per q-block walks its map row and writes
+// the chunk (or run) list; (2) plan_items_kernel -- one CTA per head: work items from the row sizes and list lengths.
+__global__ void __launch_bounds__(64)
+plan_lists_kernel(const uint8_t* __restrict__ map, const int* __restrict__ row_sz, const int* __restrict__ col_sz,
+                  int QC, int KC, int chunk_cap, int gather, int2* __restrict__ chunks, int* __restrict__ nch_of,
+                  int* __restrict__ tot_of) {
+  // gather form: the list holds RUNS {start, keys before this run} plus a sentinel {0, total}; the kernel then
+  // gathers exactly-full 128-key chunks across run boundaries.
   extern __shared__ int sm[];
-  int* coloff = sm;                 // KC + 1
-  int* rowoff = coloff + KC + 1;    // QC + 1
-  int* itembase = rowoff + QC + 1;  // QC + 1 : first two-tile item of the q-block (gather: first item)
-  int* nch_of = itembase + QC + 1;  // QC     : chunk count of the q-block's list
-  int* tail_of = nch_of + QC;       // QC     : rows of the single-tile tail (0 = none)
-  __shared__ int s_total2, s_ntails;
-  const int bh = blockIdx.x;
+  int* coloff = sm;  // KC + 1
+  const int bh = blockIdx.y;
   row_sz += static_cast<size_t>(bh) * QC;
   col_sz += static_cast<size_t>(bh) * KC;
-  const bool pair = !gather && pair_tails;
-  if (threadIdx.x == 0) {
+  // exclusive prefix sum of the key-block sizes: per-thread partial sums over a contiguous slice, then a serial
+  // pass over the 64 partials
+  __shared__ int part[64];
+  const int per = (KC + 63) / 64;
+  {
     int acc = 0;
-    for (int j = 0; j < KC; ++j) {
-      coloff[j] = acc;
-      acc += col_sz[j];
-    }
-    coloff[KC] = acc;
-  }
-  if (threadIdx.x == 32) {
-    int acc = 0, it = 0, nt = 0;
-    for (int i = 0; i < QC; ++i) {
-      rowoff[i] = acc;
-      itembase[i] = it;
-      const int r = row_sz[i];
-      acc += r;
-      const int rem = r % kItemRows;
-      int tail = 0;
-      if (pair && rem > 0 && rem <= kTileRows) tail = rem;
-      tail_of[i] = tail;
-      nt += tail > 0;
-      it += tail > 0 ? r / kItemRows : (r + kItemRows - 1) / kItemRows;
-    }
-    rowoff[QC] = acc;
-    itembase[QC] = it;
-    s_total2 = it;
-    s_ntails = nt;
-    const int total = it + (nt + 1) / 2;
-    counts[bh] = total < max_items ? total : max_items;
+    for (int j = threadIdx.x * per; j < min(KC, (static_cast<int>(threadIdx.x) + 1) * per); ++j) acc += col_sz[j];
+    part[threadIdx.x] = acc;
   }
   __syncthreads();
-  for (int qb = threadIdx.x; qb < QC; qb += blockDim.x) {
-    const int r = rowoff[qb + 1] - rowoff[qb];
-    nch_of[qb] = 0;
-    if (r == 0) continue;
-    const size_t list = (static_cast<size_t>(bh) * QC + qb) * chunk_cap;
-    int2* out = chunks + list;
-    const uint8_t* mrow = map + (static_cast<size_t>(bh) * QC + qb) * KC;
-    int n = 0, total = 0;
+  {
+    int base = 0;
+    for (int t = 0; t < static_cast<int>(threadIdx.x); ++t) base += part[t];
+    for (int j = threadIdx.x * per; j < min(KC, (static_cast<int>(threadIdx.x) + 1) * per); ++j) {
+      coloff[j] = base;
+      base += col_sz[j];
+    }
+    if (threadIdx.x == 63) coloff[KC] = base;
+  }
+  __syncthreads();
+  const int qb = blockIdx.x * 64 + threadIdx.x;
+  if (qb >= QC) return;
+  const size_t list = (static_cast<size_t>(bh) * QC + qb) * chunk_cap;
+  int2* out = chunks + list;
+  const uint8_t* mrow = map + (static_cast<size_t>(bh) * QC + qb) * KC;
+  int n = 0, total = 0;
+  if (row_sz[qb] > 0) {
     int run_s = -1, run_e = -1;
     for (int j = 0; j <= KC; ++j) {
       bool sel = false;
@@ -107,21 +84,71 @@ __global__ void plan_varblock_kernel(const uint8_t* __restrict__ map, const int*
       }
     }
     if (gather) out[n] = make_int2(0, total);  // sentinel: ends the last run
-    nch_of[qb] = n;
+  }
+  nch_of[static_cast<size_t>(bh) * QC + qb] = n;
+  tot_of[static_cast<size_t>(bh) * QC + qb] = total;
+}
+
+__global__ void plan_items_kernel(const int* __restrict__ row_sz, const int* __restrict__ nch_all,
+                                  const int* __restrict__ tot_all, int QC, int max_items, int chunk_cap,
+                                  int pair_tails, int* __restrict__ counts, int4* __restrict__ items,
+                                  int4* __restrict__ items2, int* __restrict__ item_total) {
+  // TMA form (items2 != nullptr): a q-block of r rows becomes r/256 two-tile items (+ one more when r % 256 > 128,
+  // its second tile partial) and, when 0 < r % 256 <= 128, a single-tile TAIL.  Tails are where k-means clusters
+  // lose tensor-core rows (a 297-row cluster = 256 + 41) and a lone single-tile CTA leaves half of the softmax
+  // warps idle, so the tails of a head are sorted by chunk count and packed two per CTA as DUAL items
+  // (items[i] = stream of T0, items2[i] = stream of T1; see AttnArgs::items2).  Launch order: two-tile items in
+  // q-block order, then the dual items from long to short.
+  const bool gather = item_total != nullptr;
+  extern __shared__ int sm[];
+  int* rowoff = sm;                 // QC + 1
+  int* itembase = rowoff + QC + 1;  // QC + 1 : first two-tile item of the q-block (gather: first item)
+  int* tail_of = itembase + QC + 1; // QC     : rows of the single-tile tail (0 = none)
+  int* nch_of = tail_of + QC;       // QC
+  __shared__ int s_total2, s_ntails;
+  const int bh = blockIdx.x;
+  row_sz += static_cast<size_t>(bh) * QC;
+  const bool pair = !gather && pair_tails;
+  for (int i = threadIdx.x; i < QC; i += blockDim.x) nch_of[i] = nch_all[static_cast<size_t>(bh) * QC + i];
+  if (threadIdx.x == 32) {
+    int acc = 0, it = 0, nt = 0;
+    for (int i = 0; i < QC; ++i) {
+      rowoff[i] = acc;
+      itembase[i] = it;
+      const int r = row_sz[i];
+      acc += r;
+      const int rem = r % kItemRows;
+      int tail = 0;
+      if (pair && rem > 0 && rem <= kTileRows) tail = rem;
+      tail_of[i] = tail;
+      nt += tail > 0;
+      it += tail > 0 ? r / kItemRows : (r + kItemRows - 1) / kItemRows;
+    }
+    rowoff[QC] = acc;
+    itembase[QC] = it;
+    s_total2 = it;
+    s_ntails = nt;
+    const int total = it + (nt + 1) / 2;
+    counts[bh] = total < max_items ? total : max_items;
+  }
+  __syncthreads();
+  for (int qb = threadIdx.x; qb < QC; qb += blockDim.x) {
+    const int r = rowoff[qb + 1] - rowoff[qb];
+    if (r == 0) continue;
+    const size_t list = (static_cast<size_t>(bh) * QC + qb) * chunk_cap;
+    const int n = nch_of[qb];
     const int nit = tail_of[qb] > 0 ? r / kItemRows : (r + kItemRows - 1) / kItemRows;
     for (int t = 0; t < nit; ++t) {
       const int idx = itembase[qb] + t;
       if (idx < max_items) {
         items[static_cast<size_t>(bh) * max_items + idx] =
-            make_int4(rowoff[qb] + t * kItemRows, min(kItemRows, r - t * kItemRows),
-                      static_cast<int>(list), n);
+            make_int4(rowoff[qb] + t * kItemRows, min(kItemRows, r - t * kItemRows), static_cast<int>(list), n);
         if (items2) items2[static_cast<size_t>(bh) * max_items + idx] = make_int4(0, 0, 0, 0);
-        if (gather) item_total[static_cast<size_t>(bh) * max_items + idx] = total;
+        if (gather) item_total[static_cast<size_t>(bh) * max_items + idx] = tot_all[static_cast<size_t>(bh) * QC + qb];
       }
     }
   }
   if (!pair) return;
-  __syncthreads();
   // tails: rank by (chunk count descending, q-block ascending); ranks 2i and 2i+1 share dual item i
   const int ntails = s_ntails, base = s_total2;
   for (int qb = threadIdx.x; qb < QC; qb += blockDim.x) {
@@ -445,7 +472,8 @@ int svgb_attn_plan_varblock_bytes(int BH, int S, int QC, int KC, size_t* bytes) 
   const size_t chunks = align_up(sizeof(int2) * static_cast<size_t>(BH) * QC * varblock_chunk_cap(S, KC), 256);
   // aux: TMA plans = second stream of dual items (int4 per item); gather plans = selected keys per item (int)
   const size_t aux = align_up(sizeof(int4) * BH * varblock_max_items(S, QC), 256);
-  *bytes = counts + items + chunks + aux;
+  const size_t lens = 2 * align_up(sizeof(int) * static_cast<size_t>(BH) * QC, 256);  // per q-block list length / key total
+  *bytes = counts + items + chunks + aux + lens;
   return 0;
 }
 
@@ -476,14 +504,22 @@ static int plan_varblock_impl(const uint8_t* map, const int32_t* row_sz, const i
   plan->aux_off = plan->chunks_off + align_up(sizeof(int2) * static_cast<size_t>(BH) * QC * cap, 256);
   plan->bytes = need;
   char* ws = static_cast<char*>(plan_ws);
-  const size_t smem = sizeof(int) * (KC + 1 + 2 * (QC + 1) + 2 * QC);
-  SVGB_REQUIRE(smem <= 48 * 1024, "QC/KC too large for the plan kernel (%zu B smem)", smem);
+  const size_t aux_bytes = align_up(sizeof(int4) * BH * max_items, 256);
+  int* nch_of = reinterpret_cast<int*>(ws + plan->aux_off + aux_bytes);
+  int* tot_of = nch_of + align_up(sizeof(int) * static_cast<size_t>(BH) * QC, 256) / sizeof(int);
+  const size_t smem1 = sizeof(int) * (KC + 1);
+  const size_t smem2 = sizeof(int) * (2 * (QC + 1) + 2 * QC);
+  SVGB_REQUIRE(smem1 <= 48 * 1024 && smem2 <= 48 * 1024, "QC/KC too large for the plan kernels (%zu / %zu B smem)", smem1, smem2);
   // SVGB_ATTN_PAIR=0 keeps every tail a single-tile item (A/B switch for bring-up)
   static const int pair_tails = [] { const char* e = getenv("SVGB_ATTN_PAIR"); return (e && e[0] == '0') ? 0 : 1; }();
-  plan_varblock_kernel<<<BH, 256, smem, static_cast<cudaStream_t>(stream)>>>(
-      map, row_sz, col_sz, QC, KC, max_items, cap, pair_tails, reinterpret_cast<int*>(ws + plan->counts_off),
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  plan_lists_kernel<<<dim3((QC + 63) / 64, BH), 64, smem1, st>>>(map, row_sz, col_sz, QC, KC, cap, gather ? 1 : 0,
+                                                                 reinterpret_cast<int2*>(ws + plan->chunks_off), nch_of, tot_of);
+  SVGB_LAUNCH_OK();
+  plan_items_kernel<<<BH, 256, smem2, st>>>(
+      row_sz, nch_of, tot_of, QC, max_items, cap, pair_tails, reinterpret_cast<int*>(ws + plan->counts_off),
       reinterpret_cast<int4*>(ws + plan->items_off), gather ? nullptr : reinterpret_cast<int4*>(ws + plan->aux_off),
-      reinterpret_cast<int2*>(ws + plan->chunks_off), gather ? reinterpret_cast<int*>(ws + plan->aux_off) : nullptr);
+      gather ? reinterpret_cast<int*>(ws + plan->aux_off) : nullptr);
   SVGB_LAUNCH_OK();
   return 0;
 }
@@ -591,6 +627,10 @@ static int attn_fwd_entry(const void* q, const void* k, const void* v, const flo
     if (force >= 0) a.softmax_shared = force;
   }
   a.sub_mode = 0;
+  {
+    static const int order = [] { const char* e = getenv("SVGB_ATTN_ORDER"); return (e && e[0] == '1') ? 1 : 0; }();
+    a.arrival_order = order;
+  }
   a.q_scale = q_scale;
   a.k_scale = k_scale;
   a.v_scale = v_scale;

@@ -649,6 +649,54 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
           }
         }
         tc_commit(smem_u32(&bars->o_final));
+      } else if (!kGather && ntiles == 2 && args.arrival_order) {
+        // ---- two-tile item, ARRIVAL-ORDER service (SVGB_ATTN_ORDER=1): PV_t(j) + QK_t(j+1) are issued for whichever
+        // tile's P arrives first instead of always T0 then T1, so a tile never waits behind the other one's barrier.
+        // Ring entries: K(0) = 0, V(j) = 2j+1, K(j+1) = 2j+2; V(j) / K(j+1) are released by the second tile to pass j.
+        auto bar_ready = [](uint32_t bar, uint32_t parity) -> bool {
+          uint32_t ok;
+          asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                       : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+          return ok != 0;
+        };
+        mbar_wait(smem_u32(&bars->q_full), 0, 2);
+        mbar_wait(smem_u32(&bars->kv_full[0]), 0, 3);
+        tc_fence_after();
+        {
+          const uint32_t id0 = qk_idesc(chunk_n(0));
+          issue_qk(0, k_lo0, id0);
+          tc_commit(smem_u32(&bars->s_full[0]));
+          issue_qk(1, k_lo0, id0);
+          tc_commit(smem_u32(&bars->s_full[1]));
+        }
+        tc_commit(smem_u32(&bars->kv_empty[0]));
+        int jt0 = 0, jt1 = 0;
+        while (jt0 < nchunks || jt1 < nchunks) {
+#pragma unroll
+          for (int t = 0; t < 2; ++t) {
+            const int j = t == 0 ? jt0 : jt1;
+            if (j >= nchunks) continue;
+            const bool has_next = j + 1 < nchunks;
+            const int ve = 2 * j + 1, ke = 2 * j + 2;
+            const int vslot = ve % kStages, kslot = ke % kStages;
+            if (!bar_ready(smem_u32(&bars->p_full[t]), j & 1)) continue;
+            if (!bar_ready(smem_u32(&bars->kv_full[vslot]), (ve / kStages) & 1)) continue;
+            if (has_next && !bar_ready(smem_u32(&bars->kv_full[kslot]), (ke / kStages) & 1)) continue;
+            tc_fence_after();
+            issue_pv(t, v_lo0 + vslot * kSlotStep, chunk_n(j), j > 0);
+            if (has_next) {
+              issue_qk(t, k_lo0 + kslot * kSlotStep, qk_idesc(chunk_n(j + 1)));
+              tc_commit(smem_u32(&bars->s_full[t]));
+            }
+            if ((t == 0 ? jt1 : jt0) > j) {  // the other tile is already past chunk j: its K/V tiles are free
+              tc_commit(smem_u32(&bars->kv_empty[vslot]));
+              if (has_next) tc_commit(smem_u32(&bars->kv_empty[kslot]));
+            }
+            if (t == 0) ++jt0;
+            else ++jt1;
+          }
+        }
+        tc_commit(smem_u32(&bars->o_final));
       } else {
       mbar_wait(smem_u32(&bars->q_full), 0, 2);
       if constexpr (kGather) fence_proxy_async_smem();

@@ -46,42 +46,80 @@ __device__ __forceinline__ float block_reduce(float v, float* red, bool is_max) 
   return r;
 }
 
+constexpr int kDynRows = 8;  // q-centroid rows per CTA (they share every key-centroid row read)
+
 template <bool BF16>
 __global__ void __launch_bounds__(256)
 dynmap_kernel(const uint16_t* __restrict__ qc, const uint16_t* __restrict__ kc, const int* __restrict__ k_sizes,
               int QC, int KC, int KCpad, int D, float top_p, int preserve, int log_nx, uint8_t* __restrict__ map) {
   extern __shared__ uint32_t smem[];
-  uint32_t* keys = smem;                                  // KCpad
-  float* sc = reinterpret_cast<float*>(keys + KCpad);     // KCpad : scores, then weighted exps
-  float* qrow = sc + KCpad;                               // D
-  float* red = qrow + D;                                  // 32
-  uint8_t* keep = reinterpret_cast<uint8_t*>(red + 32);   // KCpad
-  const int i = blockIdx.x, bh = blockIdx.y;
-  const uint16_t* q = qc + (static_cast<size_t>(bh) * QC + i) * D;
-  for (int d = threadIdx.x; d < D; d += blockDim.x) qrow[d] = h2f<BF16>(q[d]);
+  uint32_t* keys = smem;                                     // KCpad
+  float* sc_all = reinterpret_cast<float*>(keys + KCpad);    // kDynRows x KCpad : scores, then weighted exps / cums
+  float* qrows = sc_all + kDynRows * KCpad;                  // kDynRows x D
+  float* red = qrows + kDynRows * D;                         // 32
+  uint8_t* keep = reinterpret_cast<uint8_t*>(red + 32);      // KCpad
+  const int i0 = blockIdx.x * kDynRows, bh = blockIdx.y;
+  const int nr = min(kDynRows, QC - i0);
+  for (int e = threadIdx.x; e < kDynRows * D; e += blockDim.x) {
+    const int r = e / D, d = e - r * D;
+    qrows[e] = r < nr ? h2f<BF16>(qc[(static_cast<size_t>(bh) * QC + i0 + r) * D + d]) : 0.f;
+  }
   __syncthreads();
   const float sqrt_d = static_cast<float>(sqrt(static_cast<double>(D)));
-  float mx = -INFINITY;
-  // one warp per key centroid: a coalesced 2*D-byte row read, lanes stride the row in 32-bit pairs,
-  // fixed-order butterfly reduction (deterministic).  All QC rows of a head re-read kc from L2.
+  // Scores of kDynRows q-centroids against every key centroid: one warp per key-centroid row (a coalesced 2*D-byte
+  // read, lanes stride the row in 32-bit pairs), kDynRows dot products per row read, fixed-order butterfly reduction
+  // (deterministic; the summation order of one dot product depends neither on the unrolling nor on kDynRows).
+  // Round 1 read the whole kc of a head once per q-centroid (1000 x 256 B per CTA, 9600 CTAs hammering the same
+  // 256 KB of L2 lines: 1.37 ms); sharing each row among 8 q-centroids cuts that traffic 8x.
   {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    for (int j = warp; j < KC; j += nwarps) {
-      const uint32_t* kr = reinterpret_cast<const uint32_t*>(kc + (static_cast<size_t>(bh) * KC + j) * D);
-      float acc = 0.f;
-      for (int d2 = lane; d2 < D / 2; d2 += 32) {
-        const uint32_t w = __ldg(kr + d2);
-        acc = fmaf(qrow[2 * d2], h2f<BF16>(static_cast<uint16_t>(w & 0xffff)), acc);
-        acc = fmaf(qrow[2 * d2 + 1], h2f<BF16>(static_cast<uint16_t>(w >> 16)), acc);
+    constexpr int U = 2;
+    const int nw = D / 64;  // 32-bit words per lane and row (D <= 256)
+    float2 qv[kDynRows][2];  // this lane's q values (D <= 128 keeps them in registers; D = 192 / 256 re-read smem)
+#pragma unroll
+    for (int r = 0; r < kDynRows; ++r)
+#pragma unroll
+      for (int x = 0; x < 2; ++x)
+        qv[r][x] = x < nw ? make_float2(qrows[r * D + 2 * (lane + 32 * x)], qrows[r * D + 2 * (lane + 32 * x) + 1])
+                          : make_float2(0.f, 0.f);
+    for (int j0 = warp * U; j0 < KC; j0 += nwarps * U) {
+      uint32_t w[U][4];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int j = min(j0 + u, KC - 1);
+        const uint32_t* kr = reinterpret_cast<const uint32_t*>(kc + (static_cast<size_t>(bh) * KC + j) * D);
+#pragma unroll
+        for (int x = 0; x < 4; ++x)
+          if (x < nw) w[u][x] = __ldg(kr + lane + 32 * x);
       }
-      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-      if (lane == 0) {
-        const float m = h2f<BF16>(f2h<BF16>(acc));
-        sc[j] = h2f<BF16>(f2h<BF16>(m / sqrt_d));
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+#pragma unroll
+        for (int r = 0; r < kDynRows; ++r) {
+          float a = 0.f;
+#pragma unroll
+          for (int x = 0; x < 4; ++x)
+            if (x < nw) {
+              const int d2 = lane + 32 * x;
+              const float q0 = x < 2 ? qv[r][x & 1].x : qrows[r * D + 2 * d2];
+              const float q1 = x < 2 ? qv[r][x & 1].y : qrows[r * D + 2 * d2 + 1];
+              a = fmaf(q0, h2f<BF16>(static_cast<uint16_t>(w[u][x] & 0xffff)), a);
+              a = fmaf(q1, h2f<BF16>(static_cast<uint16_t>(w[u][x] >> 16)), a);
+            }
+          for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+          if (lane == 0 && j0 + u < KC) {
+            const float m = h2f<BF16>(f2h<BF16>(a));
+            sc_all[r * KCpad + j0 + u] = h2f<BF16>(f2h<BF16>(m / sqrt_d));
+          }
+        }
       }
     }
   }
   __syncthreads();
+  for (int rr = 0; rr < nr; ++rr) {
+  float* sc = sc_all + rr * KCpad;
+  const int i = i0 + rr;
+  float mx = -INFINITY;
   for (int j = threadIdx.x; j < KC; j += blockDim.x) mx = fmaxf(mx, sc[j]);
   mx = block_reduce(mx, red, true);
   float part = 0.f;
@@ -174,6 +212,8 @@ dynmap_kernel(const uint16_t* __restrict__ qc, const uint16_t* __restrict__ kc, 
   __syncthreads();
   uint8_t* out = map + (static_cast<size_t>(bh) * QC + i) * KC;
   for (int t = threadIdx.x; t < KC; t += blockDim.x) out[0xFFFF - (keys[t] & 0xFFFF)] = keep[t];
+  __syncthreads();  // keys / keep are reused by the next row
+  }
 }
 
 }  // namespace svgb
@@ -184,7 +224,7 @@ extern "C" int svgb_dynamic_map(const void* qc, const void* kc, const int32_t* k
                                 int KC, int D, int dtype, float top_p, int preserve, uint8_t* map,
                                 void* stream) {
   SVGB_REQUIRE(qc && kc && k_sizes && map, "null pointer");
-  SVGB_REQUIRE(BH > 0 && QC > 0 && KC > 0 && KC <= 4096 && D > 0 && D % 2 == 0, "bad sizes (KC <= 4096)");
+  SVGB_REQUIRE(BH > 0 && QC > 0 && KC > 0 && KC <= 4096 && D > 0 && D % 64 == 0 && D <= 256, "bad sizes (KC <= 4096, D in {64,128,192,256})");
   SVGB_REQUIRE(dtype == SVGB_BF16 || dtype == SVGB_F16, "dtype %d unsupported", dtype);
   int KCpad = 2;
   while (KCpad < KC) KCpad <<= 1;
@@ -195,9 +235,10 @@ extern "C" int svgb_dynamic_map(const void* qc, const void* kc, const int32_t* k
   while ((1ull << ly) < static_cast<unsigned long long>(BH) * QC) ++ly;
   uint32_t log_nx = (9u + lx - ly) / 2u;
   log_nx = log_nx < 4u ? 4u : (log_nx > 9u ? 9u : log_nx);
-  const size_t smem = sizeof(uint32_t) * KCpad + sizeof(float) * (KCpad + D + 32) + KCpad +
+  const size_t smem = sizeof(uint32_t) * KCpad + sizeof(float) * (kDynRows * (KCpad + D) + 32) + KCpad +
                       (log_nx == 4 ? 0 : sizeof(float) * (2u << log_nx) + 16);
-  dim3 grid(QC, BH);
+  SVGB_REQUIRE(smem <= 200 * 1024, "KC too large for the dynamic-map kernel (%zu B smem)", smem);
+  dim3 grid((QC + kDynRows - 1) / kDynRows, BH);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (dtype == SVGB_BF16) {
     SVGB_CUDA(cudaFuncSetAttribute(dynmap_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -282,6 +282,15 @@ kmeans_update_kernel(const uint16_t* __restrict__ x, const int* __restrict__ per
     const int* pp = perm + static_cast<size_t>(bh) * N + off;
     const uint4* xb = reinterpret_cast<const uint4*>(x) + static_cast<size_t>(bh) * N * lanes;
     int i = grp;
+    // 8 member rows in flight per thread (the gather is latency-bound: clusters are short, ~7-18 rows per group);
+    // rows are still added in ascending member order, so the result does not depend on the unrolling
+    for (; i + 7 * groups < cnt; i += 8 * groups) {
+      uint4 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = __ldg(xb + static_cast<size_t>(__ldg(pp + i + u * groups)) * lanes + w);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) add_row(v[u]);
+    }
     for (; i + 3 * groups < cnt; i += 4 * groups) {
       uint4 v[4];
 #pragma unroll

@@ -209,6 +209,7 @@ int svgb_sample_mse(const void* q, const void* k, const void* v, const int32_t* 
     a.out_f32 = 1;
     a.softmax_shared = 0;
     a.sub_mode = 0;
+    a.arrival_order = 0;
     a.q_scale = a.k_scale = a.v_scale = nullptr;
     a.gather = 0;
     a.item_total = nullptr;
