@@ -156,6 +156,12 @@ struct AttnArgs {
   // single-tile streams (<= 128 rows each, usually the tails of two different q-blocks) share one CTA -- T0 runs
   // items[i], T1 runs items2[i], each with its own chunk list and its own K/V tiles through the common ring.
   const int4* items2;
+  // variable-block plans: transposed-tail items (attn_tail.cuh): tails of <= 64 rows, two per CTA.  Same int4 format
+  // as items / items2, so they can also be run by attn_fwd_kernel as dual items when the tail kernel does not apply
+  // (head_dim 64, fp8, LSE / fp32 output).
+  const int4* titems;
+  const int4* titems2;
+  const int* tcount;
   const int* item_count;
   const int2* chunks;
   int items_stride;   // 0: one plan shared by all heads (band masks); else items per head

@@ -4,6 +4,7 @@
 
 #include "../../include/svgb200.h"
 #include "attn_kernel.cuh"
+#include "attn_tail.cuh"
 #include "host_common.h"
 
 namespace svgb {
@@ -91,45 +92,62 @@ plan_lists_kernel(const uint8_t* __restrict__ map, const int* __restrict__ row_s
 
 __global__ void plan_items_kernel(const int* __restrict__ row_sz, const int* __restrict__ nch_all,
                                   const int* __restrict__ tot_all, int QC, int max_items, int chunk_cap,
-                                  int pair_tails, int* __restrict__ counts, int4* __restrict__ items,
-                                  int4* __restrict__ items2, int* __restrict__ item_total) {
+                                  int pair_tails, int short_rows, int tmax, int* __restrict__ counts,
+                                  int4* __restrict__ items, int4* __restrict__ items2, int* __restrict__ item_total,
+                                  int4* __restrict__ titems, int4* __restrict__ titems2, int* __restrict__ tcount) {
   // TMA form (items2 != nullptr): a q-block of r rows becomes r/256 two-tile items (+ one more when r % 256 > 128,
   // its second tile partial) and, when 0 < r % 256 <= 128, a single-tile TAIL.  Tails are where k-means clusters
   // lose tensor-core rows (a 297-row cluster = 256 + 41) and a lone single-tile CTA leaves half of the softmax
   // warps idle, so the tails of a head are sorted by chunk count and packed two per CTA as DUAL items
   // (items[i] = stream of T0, items2[i] = stream of T1; see AttnArgs::items2).  Launch order: two-tile items in
-  // q-block order, then the dual items from long to short.
+  // q-block order, then the dual items from long to short.  Tails of at most `short_rows` rows go to a separate list
+  // (titems / titems2 / tcount, same format) that the transposed tail kernel runs (attn_tail.cuh).
   const bool gather = item_total != nullptr;
   extern __shared__ int sm[];
   int* rowoff = sm;                 // QC + 1
   int* itembase = rowoff + QC + 1;  // QC + 1 : first two-tile item of the q-block (gather: first item)
-  int* tail_of = itembase + QC + 1; // QC     : rows of the single-tile tail (0 = none)
-  int* nch_of = tail_of + QC;       // QC
-  __shared__ int s_total2, s_ntails;
+  int* long_of = itembase + QC + 1; // QC     : rows of the q-block's long tail (65..128; 0 = none) -> dual item
+  int* short_of = long_of + QC;     // QC     : rows of its short tail (1..short_rows; 0 = none) -> transposed kernel
+  int* nch_of = short_of + QC;      // QC
+  __shared__ int s_total2, s_nlong, s_nshort;
   const int bh = blockIdx.x;
   row_sz += static_cast<size_t>(bh) * QC;
   const bool pair = !gather && pair_tails;
   for (int i = threadIdx.x; i < QC; i += blockDim.x) nch_of[i] = nch_all[static_cast<size_t>(bh) * QC + i];
+  // split of the last r % 256 rows of a q-block (pair == true):
+  //   rem <= short                : short tail
+  //   short < rem <= 128          : long tail
+  //   128 < rem <= 128 + short    : long tail of 128 rows + short tail of rem - 128
+  //   rem > 128 + short           : one more two-tile item (second tile partial)
   if (threadIdx.x == 32) {
-    int acc = 0, it = 0, nt = 0;
+    int acc = 0, it = 0, nl = 0, ns = 0;
     for (int i = 0; i < QC; ++i) {
       rowoff[i] = acc;
       itembase[i] = it;
       const int r = row_sz[i];
       acc += r;
       const int rem = r % kItemRows;
-      int tail = 0;
-      if (pair && rem > 0 && rem <= kTileRows) tail = rem;
-      tail_of[i] = tail;
-      nt += tail > 0;
-      it += tail > 0 ? r / kItemRows : (r + kItemRows - 1) / kItemRows;
+      int lg = 0, sh = 0, n2 = (r + kItemRows - 1) / kItemRows;
+      if (pair && rem > 0) {
+        if (rem <= short_rows) sh = rem;
+        else if (rem <= kTileRows) lg = rem;
+        else if (rem <= kTileRows + short_rows) { lg = kTileRows; sh = rem - kTileRows; }
+        if (lg > 0 || sh > 0) n2 = r / kItemRows;
+      }
+      long_of[i] = lg;
+      short_of[i] = sh;
+      nl += lg > 0;
+      ns += sh > 0;
+      it += n2;
     }
     rowoff[QC] = acc;
     itembase[QC] = it;
     s_total2 = it;
-    s_ntails = nt;
-    const int total = it + (nt + 1) / 2;
+    s_nlong = nl;
+    s_nshort = ns;
+    const int total = it + (nl + 1) / 2;
     counts[bh] = total < max_items ? total : max_items;
+    if (tcount) tcount[bh] = min((ns + 1) / 2, tmax);
   }
   __syncthreads();
   for (int qb = threadIdx.x; qb < QC; qb += blockDim.x) {
@@ -137,7 +155,7 @@ __global__ void plan_items_kernel(const int* __restrict__ row_sz, const int* __r
     if (r == 0) continue;
     const size_t list = (static_cast<size_t>(bh) * QC + qb) * chunk_cap;
     const int n = nch_of[qb];
-    const int nit = tail_of[qb] > 0 ? r / kItemRows : (r + kItemRows - 1) / kItemRows;
+    const int nit = itembase[qb + 1] - itembase[qb];
     for (int t = 0; t < nit; ++t) {
       const int idx = itembase[qb] + t;
       if (idx < max_items) {
@@ -149,25 +167,33 @@ __global__ void plan_items_kernel(const int* __restrict__ row_sz, const int* __r
     }
   }
   if (!pair) return;
-  // tails: rank by (chunk count descending, q-block ascending); ranks 2i and 2i+1 share dual item i
-  const int ntails = s_ntails, base = s_total2;
-  for (int qb = threadIdx.x; qb < QC; qb += blockDim.x) {
-    const int tail = tail_of[qb];
-    if (tail == 0) continue;
-    const int mine = nch_of[qb];
-    int rank = 0;
-    for (int o = 0; o < QC; ++o)
-      if (tail_of[o] > 0 && (nch_of[o] > mine || (nch_of[o] == mine && o < qb))) ++rank;
-    const int r = rowoff[qb + 1] - rowoff[qb];
-    const int4 it = make_int4(rowoff[qb] + (r / kItemRows) * kItemRows, tail,
-                              static_cast<int>((static_cast<size_t>(bh) * QC + qb) * chunk_cap), mine);
-    const int idx = base + (rank >> 1);
-    if (idx < max_items) {
-      if ((rank & 1) == 0) {
-        items[static_cast<size_t>(bh) * max_items + idx] = it;
-        if (rank == ntails - 1) items2[static_cast<size_t>(bh) * max_items + idx] = make_int4(0, 0, 0, 0);  // odd one out
-      } else {
-        items2[static_cast<size_t>(bh) * max_items + idx] = it;
+  // tails of each class (long -> dual items of the main kernel, short -> transposed kernel): rank by (chunk count
+  // descending, q-block ascending); ranks 2i and 2i+1 share CTA i
+  const int base = s_total2;
+  for (int cls = 0; cls < 2; ++cls) {
+    const int* rows_of = cls == 0 ? long_of : short_of;
+    const int n_class = cls == 0 ? s_nlong : s_nshort;
+    int4* a = cls == 0 ? items + static_cast<size_t>(bh) * max_items + base : titems + static_cast<size_t>(bh) * tmax;
+    int4* b = cls == 0 ? items2 + static_cast<size_t>(bh) * max_items + base : titems2 + static_cast<size_t>(bh) * tmax;
+    const int cap = cls == 0 ? max_items - base : tmax;
+    for (int qb = threadIdx.x; qb < QC; qb += blockDim.x) {
+      const int rows = rows_of[qb];
+      if (rows == 0) continue;
+      const int mine = nch_of[qb];
+      int rank = 0;
+      for (int o = 0; o < QC; ++o)
+        if (rows_of[o] > 0 && (nch_of[o] > mine || (nch_of[o] == mine && o < qb))) ++rank;
+      const int r = rowoff[qb + 1] - rowoff[qb];
+      const int off = (r / kItemRows) * kItemRows + ((cls == 1 && long_of[qb] > 0) ? kTileRows : 0);
+      const int4 it = make_int4(rowoff[qb] + off, rows, static_cast<int>((static_cast<size_t>(bh) * QC + qb) * chunk_cap), mine);
+      const int idx = rank >> 1;
+      if (idx < cap) {
+        if ((rank & 1) == 0) {
+          a[idx] = it;
+          if (rank == n_class - 1) b[idx] = make_int4(0, 0, 0, 0);  // odd one out
+        } else {
+          b[idx] = it;
+        }
       }
     }
   }
@@ -456,7 +482,47 @@ int attn_fwd_impl(const void* q, int Sq, long long q_rs, long long q_hs, const v
                             : launch_attn<64, DT_F16>(qm, km, vm, a, grid, st);
 }
 
+// transposed tail kernel launch (attn_tail.cuh): bf16 / fp16, head_dim 128, 16-bit output without LSE
+int attn_tail_impl(const void* q, int Sq, long long q_rs, long long q_hs, const void* k, const void* v, int Skv,
+                   long long kv_rs, long long kv_hs, int dtype, int BH, const AttnArgs& a, int grid_x, cudaStream_t st) {
+  CUtensorMap qm, km, vm;
+  if (encode_tmap_hsd(&qm, q, dtype, BH, Sq, 128, q_rs, q_hs, kTailRows)) return -1;
+  if (encode_tmap_hsd(&km, k, dtype, BH, Skv, 128, kv_rs, kv_hs)) return -1;
+  if (encode_tmap_hsd(&vm, v, dtype, BH, Skv, 128, kv_rs, kv_hs)) return -1;
+  dim3 grid(grid_x, BH);
+  if (dtype == SVGB_BF16) {
+    auto kern = attn_tail_kernel<DT_BF16>;
+    SVGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TailCfg<DT_BF16>::kSmemBytes));
+    kern<<<grid, 384, TailCfg<DT_BF16>::kSmemBytes, st>>>(qm, km, vm, a);
+  } else {
+    auto kern = attn_tail_kernel<DT_F16>;
+    SVGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TailCfg<DT_F16>::kSmemBytes));
+    kern<<<grid, 384, TailCfg<DT_F16>::kSmemBytes, st>>>(qm, km, vm, a);
+  }
+  SVGB_LAUNCH_OK();
+  return 0;
+}
+
 static int varblock_chunk_cap(int S, int KC) { return S / kChunkCols + (KC + 1) / 2 + 2; }
+
+// scratch + transposed-tail lists that follow the aux region of a variable-block plan workspace
+struct VarTailLayout {
+  size_t nch_off, tot_off, t1_off, t2_off, tc_off;
+  int tmax;
+};
+static VarTailLayout var_tail_layout(long long aux_off, int BH, int max_items, int QC) {
+  VarTailLayout L;
+  const size_t aux_bytes = align_up(sizeof(int4) * BH * max_items, 256);
+  const size_t len_bytes = align_up(sizeof(int) * static_cast<size_t>(BH) * QC, 256);
+  L.tmax = (QC + 1) / 2;
+  const size_t t_bytes = align_up(sizeof(int4) * static_cast<size_t>(BH) * L.tmax, 256);
+  L.nch_off = aux_off + aux_bytes;
+  L.tot_off = L.nch_off + len_bytes;
+  L.t1_off = L.tot_off + len_bytes;
+  L.t2_off = L.t1_off + t_bytes;
+  L.tc_off = L.t2_off + t_bytes;
+  return L;
+}
 static int varblock_max_items(int S, int QC) { return S / kItemRows + QC + 1; }
 
 }  // namespace svgb
@@ -473,7 +539,9 @@ int svgb_attn_plan_varblock_bytes(int BH, int S, int QC, int KC, size_t* bytes) 
   // aux: TMA plans = second stream of dual items (int4 per item); gather plans = selected keys per item (int)
   const size_t aux = align_up(sizeof(int4) * BH * varblock_max_items(S, QC), 256);
   const size_t lens = 2 * align_up(sizeof(int) * static_cast<size_t>(BH) * QC, 256);  // per q-block list length / key total
-  *bytes = counts + items + chunks + aux + lens;
+  // transposed-tail items: two int4 arrays of (QC+1)/2 pairs per head + a count per head
+  const size_t tails = 2 * align_up(sizeof(int4) * static_cast<size_t>(BH) * ((QC + 1) / 2), 256) + align_up(sizeof(int) * BH, 256);
+  *bytes = counts + items + chunks + aux + lens + tails;
   return 0;
 }
 
@@ -504,11 +572,12 @@ static int plan_varblock_impl(const uint8_t* map, const int32_t* row_sz, const i
   plan->aux_off = plan->chunks_off + align_up(sizeof(int2) * static_cast<size_t>(BH) * QC * cap, 256);
   plan->bytes = need;
   char* ws = static_cast<char*>(plan_ws);
-  const size_t aux_bytes = align_up(sizeof(int4) * BH * max_items, 256);
-  int* nch_of = reinterpret_cast<int*>(ws + plan->aux_off + aux_bytes);
-  int* tot_of = nch_of + align_up(sizeof(int) * static_cast<size_t>(BH) * QC, 256) / sizeof(int);
+  const VarTailLayout tl = var_tail_layout(plan->aux_off, BH, max_items, QC);
+  int* nch_of = reinterpret_cast<int*>(ws + tl.nch_off);
+  int* tot_of = reinterpret_cast<int*>(ws + tl.tot_off);
+  plan->m2 = gather ? 0 : QC;  // lets the launcher find the transposed-tail lists (var_tail_layout)
   const size_t smem1 = sizeof(int) * (KC + 1);
-  const size_t smem2 = sizeof(int) * (2 * (QC + 1) + 2 * QC);
+  const size_t smem2 = sizeof(int) * (2 * (QC + 1) + 3 * QC);
   SVGB_REQUIRE(smem1 <= 48 * 1024 && smem2 <= 48 * 1024, "QC/KC too large for the plan kernels (%zu / %zu B smem)", smem1, smem2);
   // SVGB_ATTN_PAIR=0 keeps every tail a single-tile item (A/B switch for bring-up)
   static const int pair_tails = [] { const char* e = getenv("SVGB_ATTN_PAIR"); return (e && e[0] == '0') ? 0 : 1; }();
@@ -516,10 +585,14 @@ static int plan_varblock_impl(const uint8_t* map, const int32_t* row_sz, const i
   plan_lists_kernel<<<dim3((QC + 63) / 64, BH), 64, smem1, st>>>(map, row_sz, col_sz, QC, KC, cap, gather ? 1 : 0,
                                                                  reinterpret_cast<int2*>(ws + plan->chunks_off), nch_of, tot_of);
   SVGB_LAUNCH_OK();
+  // SVGB_ATTN_TAIL=0 keeps short tails in the main kernel's dual items (A/B switch for bring-up)
+  static const int short_rows = [] { const char* e = getenv("SVGB_ATTN_TAIL"); return (e && e[0] == '0') ? 0 : kTailRows; }();
   plan_items_kernel<<<BH, 256, smem2, st>>>(
-      row_sz, nch_of, tot_of, QC, max_items, cap, pair_tails, reinterpret_cast<int*>(ws + plan->counts_off),
-      reinterpret_cast<int4*>(ws + plan->items_off), gather ? nullptr : reinterpret_cast<int4*>(ws + plan->aux_off),
-      gather ? reinterpret_cast<int*>(ws + plan->aux_off) : nullptr);
+      row_sz, nch_of, tot_of, QC, max_items, cap, pair_tails, gather ? 0 : short_rows, tl.tmax,
+      reinterpret_cast<int*>(ws + plan->counts_off), reinterpret_cast<int4*>(ws + plan->items_off),
+      gather ? nullptr : reinterpret_cast<int4*>(ws + plan->aux_off),
+      gather ? reinterpret_cast<int*>(ws + plan->aux_off) : nullptr, reinterpret_cast<int4*>(ws + tl.t1_off),
+      reinterpret_cast<int4*>(ws + tl.t2_off), reinterpret_cast<int*>(ws + tl.tc_off));
   SVGB_LAUNCH_OK();
   return 0;
 }
@@ -643,8 +716,28 @@ static int attn_fwd_entry(const void* q, const void* k, const void* v, const flo
   a.v_ptr = v;
   a.in_row_stride = row_stride;
   a.in_head_stride = head_stride;
-  return attn_fwd_impl(q, S, row_stride, head_stride, k, v, S, row_stride, head_stride, dtype, BH, D, a,
-                       plan->max_items, static_cast<cudaStream_t>(stream));
+  a.titems = a.titems2 = nullptr;
+  a.tcount = nullptr;
+  if (attn_fwd_impl(q, S, row_stride, head_stride, k, v, S, row_stride, head_stride, dtype, BH, D, a,
+                    plan->max_items, static_cast<cudaStream_t>(stream)))
+    return -1;
+  if (plan->kind == 1 && plan->m2 > 0) {
+    // short tails (<= 64 rows) of the variable-block plan: transposed kernel when it applies, otherwise the same
+    // lists go through the main kernel as dual items
+    const VarTailLayout tl = var_tail_layout(plan->aux_off, plan->BH, plan->max_items, plan->m2);
+    AttnArgs t = a;
+    t.items = reinterpret_cast<const int4*>(ws + tl.t1_off);
+    t.items2 = reinterpret_cast<const int4*>(ws + tl.t2_off);
+    t.item_count = reinterpret_cast<const int*>(ws + tl.tc_off);
+    t.items_stride = plan->items_stride ? tl.tmax : 0;
+    const bool transposed = D == 128 && (dtype == SVGB_BF16 || dtype == SVGB_F16) && !lse;
+    if (transposed)
+      return attn_tail_impl(q, S, row_stride, head_stride, k, v, S, row_stride, head_stride, dtype, BH, t, tl.tmax,
+                            static_cast<cudaStream_t>(stream));
+    return attn_fwd_impl(q, S, row_stride, head_stride, k, v, S, row_stride, head_stride, dtype, BH, D, t, tl.tmax,
+                         static_cast<cudaStream_t>(stream));
+  }
+  return 0;
 }
 
 int svgb_attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse,

@@ -190,6 +190,8 @@ int svgb_sample_mse(const void* q, const void* k, const void* v, const int32_t* 
     AttnArgs a;
     a.items = reinterpret_cast<const int4*>(w + L.items);
     a.items2 = nullptr;
+    a.titems = a.titems2 = nullptr;
+    a.tcount = nullptr;
     a.item_count = reinterpret_cast<const int*>(w + L.counts);
     a.chunks = reinterpret_cast<const int2*>(w + (var == 0 ? L.chunks_plain : L.chunks_elem));
     a.items_stride = 0;

@@ -36,7 +36,11 @@ class HeadParallel:
     def streams(self, device, compute_streams: int = 2):
         """(communication stream, compute side streams), created on first use."""
         if self._comm_stream is None:
-            self._comm_stream = torch.cuda.Stream(device=device)
+            # HIGH priority: the attention kernel fills every SM (1 CTA / SM, the whole register file), so an NCCL
+            # kernel on a default-priority stream only gets SMs when the attention grid drains -- the N = 8 timeline
+            # of round 2 showed all three per-head all-gathers running back to back AFTER the last head (1.36 ms
+            # exposed of 8.8).  With priority the block scheduler hands freed SMs to the waiting NCCL CTAs first.
+            self._comm_stream = torch.cuda.Stream(device=device, priority=-1)
             self._compute_streams = [torch.cuda.Stream(device=device) for _ in range(max(1, compute_streams))]
         return self._comm_stream, self._compute_streams
 

@@ -48,9 +48,9 @@ fn = _lib.lib().svgb_debug_attn_trace
 fn.argtypes = [C.POINTER(C.c_longlong), C.c_int]
 assert fn(buf, 1536) == 0
 tr = [[[buf[(r * 64 + j) * 8 + e] for e in range(8)] for j in range(64)] for r in range(3)]
-t0 = min(x for x in tr[2][2] if x > 0) if any(tr[2][2]) else 0
-rows = [{"j": j, "w4": [x - t0 for x in tr[0][j][:7]], "w8": [x - t0 for x in tr[1][j][:7]],
-         "mma": [x - t0 for x in tr[2][j][:7]]} for j in range(2, 60)]
+t0 = min([x for x in tr[0][2] if x > 0] or [0])
+rows = [{"j": j, "w4": [x - t0 for x in tr[0][j][:8]], "w8": [x - t0 for x in tr[1][j][:8]],
+         "mma": [x - t0 for x in tr[2][j][:8]]} for j in range(2, 60)]
 (ROOT / "gpurun_out").mkdir(exist_ok=True)
 (ROOT / "gpurun_out" / f"attn_trace_{CASE}_{TAG}.json").write_text(json.dumps(
     {"case": CASE, "tag": TAG, "softmax_events": ["wait_S", "S_ready", "ld_done", "max(+exchange)_done", "exp_done", "st_done", "arrived"],
@@ -69,6 +69,6 @@ def period(role, ev, lo=6, hi=50):
 
 for role in ("w4", "w8"):
     print(CASE, TAG, role, "wait", d(role, 0, 1), "ld", d(role, 1, 2), "max", d(role, 2, 3), "exp", d(role, 3, 4), "st", d(role, 4, 5),
-          "arrive", d(role, 5, 6), "| step period", period(role, 0))
+          "arrive", d(role, 5, 6), "e6-7", d(role, 6, 7), "| step period", period(role, 0))
 print(CASE, TAG, "mma: waitP", d("mma", 0, 1), "issue1", d("mma", 1, 2), "issue2", d("mma", 2, 3), "e3-4", d("mma", 3, 4), "e4-5", d("mma", 4, 5),
       "e5-6", d("mma", 5, 6), "| period", period("mma", 0))
