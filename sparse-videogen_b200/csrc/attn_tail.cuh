@@ -15,6 +15,13 @@
 // per-thread partial sums over all chunks and reduced once in the epilogue.  P^T goes to shared memory (it is the B
 // operand of the second MMA; only A may live in TMEM) in the MN-major 128-byte-swizzled image a V tile has.
 //
+// Measured variants (one B200 box, QC=400 / KC=1000 rho 0.30, profiles/r02_tail_ab.txt): this version 809 TF/s (M=128
+// tiles only: 707); replacing the 48 redux by a halving shuffle butterfly + serving the two tails' MMAs in arrival order
+// + splitting the exp sweep: 765 -- the per-chunk step of a tail pair stayed at 4.1-4.7 k cycles (timeline in
+// profiles/r02_attn_timelines_summary.txt: column maxima ~1.1 k, barriers + combine ~0.45 k, exp + P stores 1.0-1.4 k),
+// i.e. ~4.4 cycles per instruction with one softmax warp per tail and sub-partition: the step is bound by dependent-issue
+// latency, more tails (warps) per CTA is the lever, not fewer instructions.
+//
 // One CTA = two tails (T0 / T1, each with its own rows, chunk list and K/V tiles through the common ring, same ring
 // order as the dual items of attn_fwd_kernel).  12 warps: warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM
 // allocator, warps 4-7 softmax of T0, warps 8-11 softmax of T1.  bf16 / fp16, D = 128.

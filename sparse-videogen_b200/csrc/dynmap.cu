@@ -46,7 +46,11 @@ __device__ __forceinline__ float block_reduce(float v, float* red, bool is_max) 
   return r;
 }
 
-constexpr int kDynRows = 8;  // q-centroid rows per CTA (they share every key-centroid row read)
+// q-centroid rows per CTA (they share every key-centroid row read).  Measured at 24 x 400 x 1000 (ncu,
+// profiles/r02_dynmap_ncu_summary.json): the kernel is INSTRUCTION-bound (1.06e9 warp instructions, issue slots 71 % busy,
+// L2 0.6 %): ~85 % of them are the 55-pass bitonic sort, the scan and the scatter of each row, so sharing the key reads
+// among 8 rows (1.53 ms) loses to one row per CTA (1.28 ms), which keeps 8 CTAs per SM resident.
+constexpr int kDynRows = 1;
 
 template <bool BF16>
 __global__ void __launch_bounds__(256)
@@ -69,11 +73,10 @@ dynmap_kernel(const uint16_t* __restrict__ qc, const uint16_t* __restrict__ kc, 
   // Scores of kDynRows q-centroids against every key centroid: one warp per key-centroid row (a coalesced 2*D-byte
   // read, lanes stride the row in 32-bit pairs), kDynRows dot products per row read, fixed-order butterfly reduction
   // (deterministic; the summation order of one dot product depends neither on the unrolling nor on kDynRows).
-  // Round 1 read the whole kc of a head once per q-centroid (1000 x 256 B per CTA, 9600 CTAs hammering the same
-  // 256 KB of L2 lines: 1.37 ms); sharing each row among 8 q-centroids cuts that traffic 8x.
+  // U key rows are in flight per warp (with one row per iteration the phase waited on two dependent L2 loads).
   {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    constexpr int U = 2;
+    constexpr int U = kDynRows == 1 ? 4 : 2;  // key rows in flight per warp
     const int nw = D / 64;  // 32-bit words per lane and row (D <= 256)
     float2 qv[kDynRows][2];  // this lane's q values (D <= 128 keeps them in registers; D = 192 / 256 re-read smem)
 #pragma unroll

@@ -211,3 +211,39 @@ def test_shd_layout_and_scatter_rows(cuda):
     expect = torch.empty_like(ref)
     expect[0].scatter_(1, perm.long()[:, :, None].expand(-1, -1, D), ref[0])
     torch.testing.assert_close(o2, expect, atol=1e-2, rtol=1e-2)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("layout", ["bhsd", "shd"])
+def test_transposed_tail_kernel_edge_sizes(cuda, dtype, layout):
+    """Short tails (<= 64 rows) of a variable-block plan run through attn_tail_kernel (keys on M, query rows on N).
+    q-block sizes are chosen to hit every split of `r % 256` (plan_items_kernel): pure short tails of 1 / 15 / 16 / 17 /
+    33 / 48 / 64 rows, a long tail (65..128), 128 + short, a partial two-tile item, an empty q-block, a q-block that
+    selects no key block at all (-> zeros) and an odd number of short tails (one CTA with a single tail); ragged key
+    blocks so that chunks have every width; output through a row scatter for the bhsd layout."""
+    from oracle.attention import dynamic_block_sparse_fwd
+    from svgb200 import core
+
+    g = torch.Generator().manual_seed(5)
+    H, D = 2, 128
+    rows = [257, 15, 64, 128 + 33, 300, 48, 17, 0, 64 + 256, 1, 16, 33, 100, 128, 200]
+    S = sum(rows)
+    row = torch.tensor([rows, rows[::-1]], dtype=torch.int32)
+    KC = 23
+    col = torch.stack([random_partition(S, KC, g) for _ in range(H)])
+    bmap = torch.rand(H, len(rows), KC, generator=g) < 0.45
+    bmap[0, 1, :] = False       # a short tail that attends nothing
+    bmap[1, 3, :] = True        # and one that attends everything
+    q, k, v = (torch.randn(1, H, S, D, generator=g).to(dtype) for _ in range(3))
+    plan = core.plan_varblock(bmap.to(cuda), row.to(cuda), col.to(cuda), S)
+    ref = dynamic_block_sparse_fwd(q, k, v, bmap[None], row[None], col[None])
+    if layout == "bhsd":
+        perm = torch.stack([torch.randperm(S, generator=g) for _ in range(H)]).to(torch.int32)
+        o = core.attn_fwd(q.to(cuda), k.to(cuda), v.to(cuda), plan, o_rows=perm.to(cuda)).float().cpu()
+        o = torch.stack([o[0, h][perm[h].long()] for h in range(H)])[None]  # undo the scatter
+    else:
+        qs, ks_, vs = (t[0].permute(1, 0, 2).contiguous().to(cuda) for t in (q, k, v))
+        o = core.attn_fwd(qs, ks_, vs, plan, layout="shd").float().cpu().permute(1, 0, 2)[None]
+    torch.testing.assert_close(o, ref, **TOL[dtype])
+    r0 = rows[0]
+    assert torch.all(o[0, 0, r0:r0 + rows[1]] == 0)
