@@ -175,6 +175,15 @@ int svgb_kmeans_update(const void* x, const int32_t* labels, const void* c_old, 
 int svgb_kmeans_run(const void* x, const void* init_centroids, int BH, int N, int K, int D, int dtype,
                     int max_iters, float tol, int32_t* labels, void* centroids_out, int32_t* counts,
                     int32_t* n_iter_out, void* ws, size_t ws_bytes, void* stream);
+/* Same loop for the caller the reference has (hyvideo/attention.py:584-626 -> :704-716): x may be a strided view
+ * (x_head_stride elements between heads, 0 = N*D; rows stay D apart) so the video part of [H, S, D] is clustered in
+ * place (the reference's `[:, :, :-context_length]` slice + `.contiguous()`), and perm_out (optional, int32 [BH,N])
+ * receives the stable argsort of the returned labels -- what the reference recomputes with torch.argsort in
+ * permute_tensor_by_labels (svg/kmeans_utils.py:829-838) -- for free: the last centroid update already built it. */
+int svgb_kmeans_run_sorted(const void* x, long long x_head_stride, const void* init_centroids, int BH, int N, int K,
+                           int D, int dtype, int max_iters, float tol, int32_t* labels, void* centroids_out,
+                           int32_t* counts, int32_t* n_iter_out, int32_t* perm_out, void* ws, size_t ws_bytes,
+                           void* stream);
 
 /* ---- mask selection --------------------------------------------------------------------- */
 /* identify_dynamic_map (svg/kmeans_utils.py:864-896): qc [BH,QC,D], kc [BH,KC,D] 16-bit,

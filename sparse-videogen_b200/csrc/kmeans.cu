@@ -1,8 +1,8 @@
 // flash-k-means for sm_100a (reference: svg/kmeans_utils.py:258-322, 375-421, 464-733).
 //
-//   assign : labels[n] = argmin_k max(0, |x_n|^2 + |c_k|^2 - 2 x_n.c_k).  X.C^T on tcgen05 (256 points
-//            per CTA = two 128-row tiles sharing every centroid tile, double-buffered TMEM accumulators),
-//            fused distance + running argmin epilogue (one thread per point).  Tensor-bound.
+//   assign : labels[n] = argmin_k max(0, |x_n|^2 + |c_k|^2 - 2 x_n.c_k).  X.C^T on tcgen05, persistent (one CTA per
+//            SM; work item = 256 points = two 128-row tiles sharing every centroid tile, double-buffered TMEM
+//            accumulators and X buffers), fused running-argmin epilogue (one thread per point).  Tensor-bound.
 //   update : deterministic segmented mean.  The reference sorts labels and uses fp32 atomics
 //            (non-deterministic order); we reuse the stable counting sort (layout_ops.cu) and sum each
 //            cluster's members in index order.  HBM-bound (x read once).
@@ -65,27 +65,78 @@ template <int D>
 struct AssignCfg {
   static constexpr int kHalves = D / 64;
   static constexpr int kPanelBytes = 128 * 128;
-  static constexpr int kTileBytes = kPanelBytes * kHalves;
-  static constexpr int kStages = 4;
-  static constexpr int kXBytes = 2 * kTileBytes;
+  static constexpr int kTileBytes = kPanelBytes * kHalves;   // 128 rows x D
+  static constexpr int kStages = 3;                          // centroid ring (128 centroids per stage)
+  static constexpr int kXBytes = 2 * kTileBytes;             // one work item = 256 points
   static constexpr int kRingBytes = kStages * kTileBytes;
-  static constexpr int kMaxK = 4096;              // whole |c|^2 row of one head lives in smem
-  static constexpr int kCsqBytes = kMaxK * 4;
-  static constexpr int kSmemBytes = 1024 + kXBytes + kRingBytes + kCsqBytes + 512;
+  static constexpr int kBarBytes = 256;
+  // 2 X buffers (the next item's points land while this item's MMAs run) + ring + barriers + alignment slack
+  static constexpr int kSmemBytes = 1024 + 2 * kXBytes + kRingBytes + kBarBytes;
+  static_assert(kSmemBytes <= 232448, "exceeds the 227 KB per-CTA shared memory of sm_100");
 };
 
 struct AssignBars {
-  uint64_t x_full;
+  uint64_t x_full[2], x_empty[2];
   uint64_t c_full[4], c_empty[4];
   uint64_t s_full[2][2], s_empty[2][2];
   uint32_t tmem_base;
 };
+static_assert(sizeof(AssignBars) <= 256, "barrier block");
 
+__device__ __forceinline__ float fmin3(float a, float b, float c) {
+  float r;
+  asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));  // FMNMX3
+  return r;
+}
+
+// |x_n|^2 of one point from the swizzled X tile in shared memory, with the reference's rounding points
+// ((x**2).sum(-1) in the 16-bit dtype, batch_kmeans_Euclid:704): 16-bit products, fp32 sum, 16-bit result.
+template <int D, bool BF16>
+__device__ __forceinline__ float row_sqnorm_smem(const uint8_t* tile, int r) {
+  float acc = 0.f;
+#pragma unroll
+  for (int h = 0; h < D / 64; ++h) {
+    const uint8_t* row = tile + h * AssignCfg<D>::kPanelBytes + r * 128;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      // 128-byte swizzle: logical 16-byte chunk c of row r sits at chunk position c ^ (r & 7)
+      const uint4 v = *reinterpret_cast<const uint4*>(row + ((c ^ (r & 7)) << 4));
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if constexpr (BF16) {
+          const __nv_bfloat162 x2 = *reinterpret_cast<const __nv_bfloat162*>(&w[i]);
+          const float2 f = __bfloat1622float2(__hmul2(x2, x2));
+          acc += f.x;
+          acc += f.y;
+        } else {
+          const __half2 x2 = *reinterpret_cast<const __half2*>(&w[i]);
+          const float2 f = __half22float2(__hmul2(x2, x2));
+          acc += f.x;
+          acc += f.y;
+        }
+      }
+    }
+  }
+  return round16<BF16>(acc);
+}
+
+// Persistent: one CTA per SM walks the (head, 256-point block) work items; warp 0 = TMA producer, warp 1 = MMA
+// issuer, warps 4-11 = two epilogue warpgroups (one per 128-point tile).  Nothing is torn down between items: the
+// centroid ring, the TMEM double buffers and their barrier phases run on one global chunk counter, and the next
+// item's points are loaded into the second X buffer while the current item's MMAs run.
+//
+// Epilogue arithmetic.  argmin_k max(0, |x|^2 + |c_k|^2 - 2 x.c_k) is taken as argmin_k of d'_k = |c_k|^2 - 2 x.c_k
+// (|x|^2 is a per-row constant and rounding is monotone, so min_k fl(d'_k + |x|^2) = fl(min_k d'_k + |x|^2)); the
+// clamp and the first-index tie rule are applied to the group minimum exactly as before.  That leaves one packed
+// FFMA2 and one FMNMX3 per two centroids (the first version spent ~4 instructions per centroid and was issue-bound).
+// x_sq == nullptr: |x|^2 is computed from the X tile in shared memory (the Lloyd loop does this: no separate pass
+// over x); otherwise the caller's values are used (svgb_kmeans_assign, where the reference passes its own x_sq).
 template <int D, bool BF16>
 __global__ void __launch_bounds__(384, 1)
 kmeans_assign_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap cmap0,
                      const __grid_constant__ CUtensorMap cmap1, const float* __restrict__ x_sq,
-                     const float* __restrict__ c_sq, int* __restrict__ labels, int N, int K,
+                     const float* __restrict__ c_sq, int* __restrict__ labels, int N, int K, int BH,
                      const KmState* __restrict__ state) {
   using Cfg = AssignCfg<D>;
   int cur = 0;
@@ -94,17 +145,15 @@ kmeans_assign_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_cons
     cur = state->cur;
   }
   const CUtensorMap* cmap = cur == 0 ? &cmap0 : &cmap1;
-  const int bh = blockIdx.y;
-  const int row0 = blockIdx.x * 256;
-  const int ntiles = (N - row0) > 128 ? 2 : 1;
   const int nchunks = (K + 127) / 128;
+  const int blocks_per_head = (N + 255) / 256;
+  const int total = BH * blocks_per_head;
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
-  const uint32_t sX = smem_base, sRing = smem_base + Cfg::kXBytes;
-  float* csq = reinterpret_cast<float*>(smem_al + Cfg::kXBytes + Cfg::kRingBytes);
-  AssignBars* bars = reinterpret_cast<AssignBars*>(smem_al + Cfg::kXBytes + Cfg::kRingBytes + Cfg::kCsqBytes);
+  const uint32_t sX = smem_base, sRing = smem_base + 2 * Cfg::kXBytes;
+  AssignBars* bars = reinterpret_cast<AssignBars*>(smem_al + 2 * Cfg::kXBytes + Cfg::kRingBytes);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
@@ -112,7 +161,10 @@ kmeans_assign_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_cons
     tma_prefetch_desc(cmap);
   }
   if (warp == 1 && lane == 0) {
-    mbar_init(smem_u32(&bars->x_full), 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(smem_u32(&bars->x_full[b]), 1);
+      mbar_init(smem_u32(&bars->x_empty[b]), 1 + 8);  // MMA commit + the 8 epilogue warps (they read |x|^2 from it)
+    }
     for (int s = 0; s < Cfg::kStages; ++s) {
       mbar_init(smem_u32(&bars->c_full[s]), 1);
       mbar_init(smem_u32(&bars->c_empty[s]), 1);
@@ -132,103 +184,147 @@ kmeans_assign_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_cons
 
   if (warp == 0) {
     if (lane == 0) {
-      const uint32_t xb = smem_u32(&bars->x_full);
-      mbar_expect_tx(xb, ntiles * Cfg::kTileBytes + nchunks * 512);
-      for (int t = 0; t < ntiles; ++t)
-        for (int h = 0; h < Cfg::kHalves; ++h)
-          tma_load_3d(sX + t * Cfg::kTileBytes + h * Cfg::kPanelBytes, &xmap, xb, h * 64, row0 + t * 128, bh);
-      // |c|^2 of the whole head (padded to a multiple of 128 floats) rides the same barrier
-      asm volatile(
-          "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-          ::"r"(smem_u32(csq)), "l"(c_sq + static_cast<size_t>(bh) * nchunks * 128), "r"(nchunks * 512),
-          "r"(xb)
-          : "memory");
-      for (int j = 0; j < nchunks; ++j) {
-        const int slot = j % Cfg::kStages;
-        mbar_wait(smem_u32(&bars->c_empty[slot]), ((j / Cfg::kStages) & 1) ^ 1, 31);
-        const uint32_t fb = smem_u32(&bars->c_full[slot]);
-        mbar_expect_tx(fb, Cfg::kTileBytes);
-        for (int h = 0; h < Cfg::kHalves; ++h)
-          tma_load_3d(sRing + slot * Cfg::kTileBytes + h * Cfg::kPanelBytes, cmap, fb, h * 64, j * 128, bh);
+      auto load_x = [&](int i, int item) {
+        const int xb = i & 1, bh = item / blocks_per_head, row0 = (item % blocks_per_head) * 256;
+        mbar_wait(smem_u32(&bars->x_empty[xb]), ((i >> 1) & 1) ^ 1, 30);
+        const uint32_t fb = smem_u32(&bars->x_full[xb]);
+        mbar_expect_tx(fb, Cfg::kXBytes);
+        for (int t = 0; t < 2; ++t) {
+          // a second tile that would start past the end is loaded from the last row instead (its labels are not
+          // stored); partially out-of-range tiles are zero-filled by TMA
+          const int r = min(row0 + t * 128, N - 1);
+          for (int h = 0; h < Cfg::kHalves; ++h)
+            tma_load_3d(sX + xb * Cfg::kXBytes + t * Cfg::kTileBytes + h * Cfg::kPanelBytes, &xmap, fb, h * 64, r, bh);
+        }
+      };
+      int g = 0, i = 0;
+      if (static_cast<int>(blockIdx.x) < total) load_x(0, blockIdx.x);
+      // the next item's points are requested once the ring has wrapped inside this item: by then the MMAs of the
+      // previous item (which release that X buffer) are known to have completed, so that wait cannot hold up this
+      // item's centroid loads
+      const int x_at = min(static_cast<int>(Cfg::kStages), nchunks);
+      for (int item = blockIdx.x; item < total; item += gridDim.x, ++i) {
+        const int bh = item / blocks_per_head;
+        const int next = item + gridDim.x;
+        for (int j = 0; j <= nchunks; ++j) {
+          const int slot = g % Cfg::kStages;
+          if (j < nchunks) mbar_wait(smem_u32(&bars->c_empty[slot]), ((g / Cfg::kStages) & 1) ^ 1, 31);
+          if (j == x_at && next < total) load_x(i + 1, next);
+          if (j < nchunks) {
+            const uint32_t fb = smem_u32(&bars->c_full[slot]);
+            mbar_expect_tx(fb, Cfg::kTileBytes);
+            for (int h = 0; h < Cfg::kHalves; ++h)
+              tma_load_3d(sRing + slot * Cfg::kTileBytes + h * Cfg::kPanelBytes, cmap, fb, h * 64, j * 128, bh);
+            ++g;
+          }
+        }
       }
     }
   } else if (warp == 1) {
     if (elect_one()) {  // elect.sync: ptxas emits the tcgen05 stream without per-instruction election loops
-      mbar_wait(smem_u32(&bars->x_full), 0, 32);
       const uint32_t idesc = make_idesc(128, 128, BF16, false, false);
       // descriptors = constant high word + running low word (address field in units of 16 B), see attn_kernel.cuh
       const uint64_t d0 = desc_kmajor_sw128(sX);
       const uint32_t hi = static_cast<uint32_t>(d0 >> 32), x_lo0 = static_cast<uint32_t>(d0);
       const uint32_t c_lo0 = static_cast<uint32_t>(desc_kmajor_sw128(sRing));
-      for (int j = 0; j < nchunks; ++j) {
-        const int slot = j % Cfg::kStages, buf = j & 1;
-        const uint32_t c_lo = c_lo0 + slot * (Cfg::kTileBytes >> 4);
-        mbar_wait(smem_u32(&bars->c_full[slot]), (j / Cfg::kStages) & 1, 33);
-        for (int t = 0; t < ntiles; ++t) {
-          mbar_wait(smem_u32(&bars->s_empty[t][buf]), ((j >> 1) & 1) ^ 1, 34);
-          tc_fence_after();
-          const uint32_t d_tmem = tmem + t * 256 + buf * 128;
-          uint32_t a_lo = x_lo0 + t * (Cfg::kTileBytes >> 4), b_lo = c_lo;
+      int g = 0, i = 0;
+      for (int item = blockIdx.x; item < total; item += gridDim.x, ++i) {
+        const int xb = i & 1;
+        mbar_wait(smem_u32(&bars->x_full[xb]), (i >> 1) & 1, 32);
+        for (int j = 0; j < nchunks; ++j, ++g) {
+          const int slot = g % Cfg::kStages, buf = g & 1;
+          const uint32_t c_lo = c_lo0 + slot * (Cfg::kTileBytes >> 4);
+          mbar_wait(smem_u32(&bars->c_full[slot]), (g / Cfg::kStages) & 1, 33);
+          for (int t = 0; t < 2; ++t) {
+            mbar_wait(smem_u32(&bars->s_empty[t][buf]), ((g >> 1) & 1) ^ 1, 34);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem + t * 256 + buf * 128;
+            uint32_t a_lo = x_lo0 + ((xb * Cfg::kXBytes + t * Cfg::kTileBytes) >> 4), b_lo = c_lo;
 #pragma unroll
-          for (int kk = 0; kk < D / 16; ++kk) {
-            mma_ss(d_tmem, (static_cast<uint64_t>(hi) << 32) | a_lo, (static_cast<uint64_t>(hi) << 32) | b_lo, idesc, kk > 0);
-            asm volatile("" : "+r"(a_lo), "+r"(b_lo));
-            const uint32_t step = ((kk & 3) == 3) ? ((Cfg::kPanelBytes - 3 * 32) >> 4) : (32 >> 4);
-            a_lo += step;
-            b_lo += step;
+            for (int kk = 0; kk < D / 16; ++kk) {
+              mma_ss(d_tmem, (static_cast<uint64_t>(hi) << 32) | a_lo, (static_cast<uint64_t>(hi) << 32) | b_lo, idesc, kk > 0);
+              asm volatile("" : "+r"(a_lo), "+r"(b_lo));
+              const uint32_t step = ((kk & 3) == 3) ? ((Cfg::kPanelBytes - 3 * 32) >> 4) : (32 >> 4);
+              a_lo += step;
+              b_lo += step;
+            }
+            tc_commit(smem_u32(&bars->s_full[t][buf]));
           }
-          tc_commit(smem_u32(&bars->s_full[t][buf]));
+          tc_commit(smem_u32(&bars->c_empty[slot]));
         }
-        tc_commit(smem_u32(&bars->c_empty[slot]));
+        tc_commit(smem_u32(&bars->x_empty[xb]));
       }
     }
   } else if (warp >= 4) {
-    const int t = (warp - 4) >> 2;
-    if (t < ntiles) {
-      const int wq = warp & 3;
-      const int n = row0 + t * 128 + wq * 32 + lane;
-      const uint32_t lane_addr = tmem + (static_cast<uint32_t>(wq * 32) << 16) + t * 256;
-      const float xs = (n < N) ? x_sq[static_cast<size_t>(bh) * N + n] : 0.f;
+    const int t = (warp - 4) >> 2, wq = warp & 3;
+    const uint32_t lane_addr = tmem + (static_cast<uint32_t>(wq * 32) << 16) + t * 256;
+    const uint64_t neg2 = pack_f32x2(-2.f, -2.f);
+    int g = 0, i = 0;
+    for (int item = blockIdx.x; item < total; item += gridDim.x, ++i) {
+      const int xb = i & 1, bh = item / blocks_per_head, row0 = (item % blocks_per_head) * 256;
+      const int r = wq * 32 + lane;
+      const int n = row0 + t * 128 + r;
+      mbar_wait(smem_u32(&bars->x_full[xb]), (i >> 1) & 1, 35);
+      float xs;
+      if (x_sq) xs = (n < N) ? x_sq[static_cast<size_t>(bh) * N + n] : 0.f;
+      else xs = row_sqnorm_smem<D, BF16>(smem_al + xb * Cfg::kXBytes + t * Cfg::kTileBytes, r);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&bars->x_empty[xb]));
+      const float4* cs_head = reinterpret_cast<const float4*>(c_sq + static_cast<size_t>(bh) * nchunks * 128);
       float best = 3.4e38f;
       int best_k = 0;
-      mbar_wait(smem_u32(&bars->x_full), 0, 35);  // |c|^2 row landed with X
-      for (int j = 0; j < nchunks; ++j) {
-        const int buf = j & 1;
-        mbar_wait(smem_u32(&bars->s_full[t][buf]), (j >> 1) & 1, 36);
+      for (int j = 0; j < nchunks; ++j, ++g) {
+        const int buf = g & 1;
+        mbar_wait(smem_u32(&bars->s_full[t][buf]), (g >> 1) & 1, 36);
         tc_fence_after();
-        const float* cs = csq + j * 128;
+        const float4* cs = cs_head + j * 32;
         const int kbase = j * 128;
-        const bool tail = kbase + 128 > K;  // only the last chunk has centroid columns past K
-#pragma unroll 1
-        for (int g = 0; g < 4; ++g) {
-          uint32_t r[32];
-          tmem_ld32(lane_addr + buf * 128 + g * 32, r);
-          tc_wait_ld();
-          // d = (|x|^2 + |c|^2) - 2 x.c  (one rounding for the sum, one for the fma, as the reference);
-          // min_k max(d_k, 0) == max(min_k d_k, 0), so the clamp is applied once to the group minimum and
-          // the running (best, argbest) is only touched when the group improves it -- O(log K) times per
-          // point -- which takes the compare/select pair out of the per-element work.
-          float dv[32];
+        uint32_t ra[32], rb[32];
+        tmem_ld32(lane_addr + buf * 128, ra);
+        auto group = [&](const uint32_t (&rr)[32], int gi) {
+          // d'_k = |c_k|^2 - 2 x.c_k ; |c|^2 comes through L1 (warp-uniform 16-byte loads, padded with +3e38 past K
+          // so that the columns TMA zero-filled can never win)
+          uint64_t dv[16];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) dv[i] = fmaf(-2.f, __uint_as_float(r[i]), xs + cs[g * 32 + i]);
-          if (tail) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (kbase + g * 32 + i >= K) dv[i] = 3.4e38f;
+          for (int q = 0; q < 8; ++q) {
+            const float4 c4 = __ldg(cs + gi * 8 + q);
+            dv[2 * q] = ffma2(pack_f32x2(__uint_as_float(rr[4 * q]), __uint_as_float(rr[4 * q + 1])), neg2,
+                              pack_f32x2(c4.x, c4.y));
+            dv[2 * q + 1] = ffma2(pack_f32x2(__uint_as_float(rr[4 * q + 2]), __uint_as_float(rr[4 * q + 3])), neg2,
+                                  pack_f32x2(c4.z, c4.w));
           }
-          float gmin = dv[0];
+          float lo, hi2;
+          unpack_f32x2(dv[0], lo, hi2);
+          float gmin = fminf(lo, hi2);
 #pragma unroll
-          for (int i = 1; i < 32; ++i) gmin = fminf(gmin, dv[i]);
-          gmin = fmaxf(gmin, 0.f);
-          if (gmin < best) {  // strict: an earlier group keeps ties; inside the group the lowest index wins
-            best = gmin;
-#pragma unroll
-            for (int i = 31; i >= 0; --i)
-              if (fmaxf(dv[i], 0.f) == gmin) best_k = kbase + g * 32 + i;
+          for (int q = 1; q < 16; ++q) {
+            unpack_f32x2(dv[q], lo, hi2);
+            gmin = fmin3(gmin, lo, hi2);
           }
-        }
+          const float gd = fmaxf(gmin + xs, 0.f);
+          if (gd < best) {  // strict: an earlier group keeps ties; inside the group the lowest index wins
+            best = gd;
+#pragma unroll
+            for (int q = 15; q >= 0; --q) {
+              unpack_f32x2(dv[q], lo, hi2);
+              if (fmaxf(hi2 + xs, 0.f) == gd) best_k = kbase + gi * 32 + 2 * q + 1;
+              if (fmaxf(lo + xs, 0.f) == gd) best_k = kbase + gi * 32 + 2 * q;
+            }
+          }
+        };
+        tc_wait_ld();
+        tmem_ld32(lane_addr + buf * 128 + 32, rb);
+        group(ra, 0);
+        tc_wait_ld();
+        tmem_ld32(lane_addr + buf * 128 + 64, ra);
+        group(rb, 1);
+        tc_wait_ld();
+        tmem_ld32(lane_addr + buf * 128 + 96, rb);
+        group(ra, 2);
+        tc_wait_ld();
         tc_fence_before();
-        mbar_arrive(smem_u32(&bars->s_empty[t][buf]));
+        mbar_arrive(smem_u32(&bars->s_empty[t][buf]));  // the accumulator is in registers: hand the buffer back early
+        group(rb, 3);
       }
       if (n < N) labels[static_cast<size_t>(bh) * N + n] = best_k;
     }
@@ -253,7 +349,7 @@ kmeans_update_kernel(const uint16_t* __restrict__ x, const int* __restrict__ per
                      const int* __restrict__ counts, const int* __restrict__ chunk0_base,
                      const uint16_t* __restrict__ c_old0, const uint16_t* __restrict__ c_old1,
                      uint16_t* __restrict__ c_new0, uint16_t* __restrict__ c_new1, float* __restrict__ shift_max,
-                     int N, int K, int D, const KmState* __restrict__ state) {
+                     int N, int K, int D, long long x_head_stride, const KmState* __restrict__ state) {
   int cur = 0;
   if (state) {
     if (state->done) return;
@@ -268,7 +364,7 @@ kmeans_update_kernel(const uint16_t* __restrict__ x, const int* __restrict__ per
   const int groups = blockDim.x / lanes;
   const int grp = threadIdx.x / lanes, w = threadIdx.x % lanes;
   __shared__ float part[32][129];
-  __shared__ float s_norm[128];
+  __shared__ float s_norm[8];
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   auto add_row = [&](const uint4& v) {
     const uint32_t ws[4] = {v.x, v.y, v.z, v.w};
@@ -280,29 +376,28 @@ kmeans_update_kernel(const uint16_t* __restrict__ x, const int* __restrict__ per
   };
   if (grp < groups) {
     const int* pp = perm + static_cast<size_t>(bh) * N + off;
-    const uint4* xb = reinterpret_cast<const uint4*>(x) + static_cast<size_t>(bh) * N * lanes;
-    int i = grp;
-    // 8 member rows in flight per thread (the gather is latency-bound: clusters are short, ~7-18 rows per group);
-    // rows are still added in ascending member order, so the result does not depend on the unrolling
-    for (; i + 7 * groups < cnt; i += 8 * groups) {
+    const uint4* xb = reinterpret_cast<const uint4*>(x + static_cast<size_t>(bh) * x_head_stride);
+    // 8 member rows in flight per thread, fully predicated (clusters are short -- ~7 rows per group at K=1000 -- so a
+    // remainder loop of single dependent index->row loads used to dominate the CTA's lifetime); rows are still added
+    // in ascending member order, so the result does not depend on the batching
+    for (int i = grp; i < cnt; i += 8 * groups) {
+      int idx[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) idx[u] = (i + u * groups < cnt) ? __ldg(pp + i + u * groups) : -1;
       uint4 v[8];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) v[u] = __ldg(xb + static_cast<size_t>(__ldg(pp + i + u * groups)) * lanes + w);
+      for (int u = 0; u < 8; ++u)
+        v[u] = idx[u] >= 0 ? __ldg(xb + static_cast<size_t>(idx[u]) * lanes + w) : make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
-      for (int u = 0; u < 8; ++u) add_row(v[u]);
+      for (int u = 0; u < 8; ++u)
+        if (idx[u] >= 0) add_row(v[u]);
     }
-    for (; i + 3 * groups < cnt; i += 4 * groups) {
-      uint4 v[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) v[u] = __ldg(xb + static_cast<size_t>(__ldg(pp + i + u * groups)) * lanes + w);
-#pragma unroll
-      for (int u = 0; u < 4; ++u) add_row(v[u]);
-    }
-    for (; i < cnt; i += groups) add_row(__ldg(xb + static_cast<size_t>(__ldg(pp + i)) * lanes + w));
 #pragma unroll
     for (int e = 0; e < 8; ++e) part[grp][w * 8 + e] = acc[e];
   }
   __syncthreads();
+  // D <= 128 threads finish the mean; the squared shift is reduced by warp shuffles (fixed order -> deterministic)
+  float sq = 0.f;
   if (static_cast<int>(threadIdx.x) < D) {
     const int d = threadIdx.x;
     float s = 0.f;
@@ -315,14 +410,18 @@ kmeans_update_kernel(const uint16_t* __restrict__ x, const int* __restrict__ per
     c_new[(static_cast<size_t>(bh) * K + k) * D + d] = bits;
     // shift = |round16(new - old)|_2, then rounded to 16 bit like the reference's bf16 tensor ops
     const float dd = round16<BF16>(n - o);
-    s_norm[d] = dd * dd;
+    sq = dd * dd;
   }
-  __syncthreads();
-  if (threadIdx.x == 0 && shift_max) {
-    float t = 0.f;
-    for (int i = 0; i < D; ++i) t += s_norm[i];
-    const float nrm = round16<BF16>(sqrtf(t));
-    atomicMax(reinterpret_cast<int*>(shift_max), __float_as_int(nrm));  // non-negative floats order as ints
+  if (shift_max) {
+    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    if ((threadIdx.x & 31) == 0) s_norm[threadIdx.x >> 5] = sq;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float t = 0.f;
+      for (int i = 0; i < (D + 31) / 32; ++i) t += s_norm[i];
+      const float nrm = round16<BF16>(sqrtf(t));
+      atomicMax(reinterpret_cast<int*>(shift_max), __float_as_int(nrm));  // non-negative floats order as ints
+    }
   }
 }
 
@@ -354,7 +453,8 @@ __global__ void csq_kernel(const uint16_t* __restrict__ c0, const uint16_t* __re
     }
   }
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-  if (lane == 0) out[static_cast<size_t>(bh) * Kpad + k] = round16<BF16>(acc);
+  // columns past K (zero-filled by TMA in the assign kernel) get a norm no point can prefer
+  if (lane == 0) out[static_cast<size_t>(bh) * Kpad + k] = k < K ? round16<BF16>(acc) : 3.0e38f;
 }
 
 __global__ void km_commit_kernel(KmState* st, float* shift_max, float tol, int it) {
@@ -385,6 +485,16 @@ __global__ void km_finalize_kernel(const KmState* st, const uint4* __restrict__ 
   if (n_iter_out && blockIdx.x == 0 && threadIdx.x == 0) *n_iter_out = st->n_iter;
 }
 
+static int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+
 template <int D, bool BF16>
 static int launch_assign(const CUtensorMap& xm, const CUtensorMap& cm0, const CUtensorMap& cm1,
                          const float* x_sq, const float* c_sq_padded, int* labels, int BH, int N, int K,
@@ -392,17 +502,18 @@ static int launch_assign(const CUtensorMap& xm, const CUtensorMap& cm0, const CU
   using Cfg = AssignCfg<D>;
   auto kern = kmeans_assign_kernel<D, BF16>;
   SVGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-  dim3 grid((N + 255) / 256, BH);
-  kern<<<grid, 384, Cfg::kSmemBytes, stream>>>(xm, cm0, cm1, x_sq, c_sq_padded, labels, N, K, st);
+  const int items = BH * ((N + 255) / 256);
+  const int grid = items < sm_count() ? items : sm_count();  // persistent: one CTA per SM
+  kern<<<grid, 384, Cfg::kSmemBytes, stream>>>(xm, cm0, cm1, x_sq, c_sq_padded, labels, N, K, BH, st);
   SVGB_LAUNCH_OK();
   return 0;
 }
 
-static int dispatch_assign(const void* x, const void* c0, const void* c1, const float* x_sq,
+static int dispatch_assign(const void* x, long long x_head_stride, const void* c0, const void* c1, const float* x_sq,
                            const float* c_sq_padded, int* labels, int BH, int N, int K, int D, int dtype,
                            const KmState* st, cudaStream_t stream) {
   CUtensorMap xm, cm0, cm1;
-  if (encode_tmap_hsd(&xm, x, dtype, BH, N, D, D, static_cast<long long>(N) * D)) return -1;
+  if (encode_tmap_hsd(&xm, x, dtype, BH, N, D, D, x_head_stride)) return -1;
   if (encode_tmap_hsd(&cm0, c0, dtype, BH, K, D, D, static_cast<long long>(K) * D)) return -1;
   if (encode_tmap_hsd(&cm1, c1, dtype, BH, K, D, D, static_cast<long long>(K) * D)) return -1;
   if (D == 128)
@@ -440,7 +551,7 @@ static int launch_csq(const void* c0, const void* c1, float* out, int BH, int K,
   return 0;
 }
 
-static int launch_update(const void* x, const int* perm, const int* counts, const int* offs, const void* c_old0,
+static int launch_update(const void* x, long long x_head_stride, const int* perm, const int* counts, const int* offs, const void* c_old0,
                          const void* c_old1, void* c_new0, void* c_new1, float* shift_max, int BH, int N, int K,
                          int D, int dtype, const KmState* st, cudaStream_t stream) {
   dim3 grid(K, BH);
@@ -451,15 +562,15 @@ static int launch_update(const void* x, const int* perm, const int* counts, cons
   auto N0 = static_cast<uint16_t*>(c_new0);
   auto N1 = static_cast<uint16_t*>(c_new1);
   if (dtype == SVGB_BF16)
-    kmeans_update_kernel<true><<<grid, threads, 0, stream>>>(X, perm, counts, offs, O0, O1, N0, N1, shift_max, N, K, D, st);
+    kmeans_update_kernel<true><<<grid, threads, 0, stream>>>(X, perm, counts, offs, O0, O1, N0, N1, shift_max, N, K, D, x_head_stride, st);
   else
-    kmeans_update_kernel<false><<<grid, threads, 0, stream>>>(X, perm, counts, offs, O0, O1, N0, N1, shift_max, N, K, D, st);
+    kmeans_update_kernel<false><<<grid, threads, 0, stream>>>(X, perm, counts, offs, O0, O1, N0, N1, shift_max, N, K, D, x_head_stride, st);
   SVGB_LAUNCH_OK();
   return 0;
 }
 
 struct KmLayout {
-  size_t csq_pad, perm, offs, sort, sort_bytes, cbuf0, cbuf1, state, xsq, total;
+  size_t csq_pad, perm, offs, sort, sort_bytes, cbuf0, cbuf1, state, total;
 };
 static KmLayout km_layout(int BH, int N, int K, int D) {
   KmLayout L;
@@ -479,7 +590,6 @@ static KmLayout km_layout(int BH, int N, int K, int D) {
   L.cbuf0 = take(2ull * BH * K * D);
   L.cbuf1 = take(2ull * BH * K * D);
   L.state = take(256);
-  L.xsq = take(sizeof(float) * static_cast<size_t>(BH) * N);
   L.total = o;
   return L;
 }
@@ -516,7 +626,7 @@ int svgb_kmeans_assign(const void* x, const void* c, const float* x_sq, int32_t*
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   float* csqp = reinterpret_cast<float*>(w + L.csq_pad);
   if (launch_csq(c, c, csqp, BH, K, D, dtype, nullptr, st)) return -1;
-  return dispatch_assign(x, c, c, x_sq, csqp, labels, BH, N, K, D, dtype, nullptr, st);
+  return dispatch_assign(x, static_cast<long long>(N) * D, c, c, x_sq, csqp, labels, BH, N, K, D, dtype, nullptr, st);
 }
 
 int svgb_kmeans_update(const void* x, const int32_t* labels, const void* c_old, void* c_new,
@@ -533,14 +643,24 @@ int svgb_kmeans_update(const void* x, const int32_t* labels, const void* c_old, 
   int* offs = reinterpret_cast<int*>(w + L.offs);
   if (argsort_labels_impl(labels, BH, N, K, perm, counts, offs, w + L.sort, nullptr, st)) return -1;
   if (shift_max) SVGB_CUDA(cudaMemsetAsync(shift_max, 0, sizeof(float), st));
-  return launch_update(x, perm, counts, offs, c_old, c_old, c_new, c_new, shift_max, BH, N, K, D, dtype, nullptr, st);
+  return launch_update(x, static_cast<long long>(N) * D, perm, counts, offs, c_old, c_old, c_new, c_new, shift_max, BH, N, K, D, dtype, nullptr, st);
 }
 
 int svgb_kmeans_run(const void* x, const void* init_centroids, int BH, int N, int K, int D, int dtype,
                     int max_iters, float tol, int32_t* labels, void* centroids_out, int32_t* counts,
                     int32_t* n_iter_out, void* ws, size_t ws_bytes, void* stream) {
+  return svgb_kmeans_run_sorted(x, 0, init_centroids, BH, N, K, D, dtype, max_iters, tol, labels, centroids_out, counts,
+                                n_iter_out, nullptr, ws, ws_bytes, stream);
+}
+
+int svgb_kmeans_run_sorted(const void* x, long long x_head_stride, const void* init_centroids, int BH, int N, int K,
+                           int D, int dtype, int max_iters, float tol, int32_t* labels, void* centroids_out,
+                           int32_t* counts, int32_t* n_iter_out, int32_t* perm_out, void* ws, size_t ws_bytes,
+                           void* stream) {
   SVGB_REQUIRE(x && init_centroids && labels && centroids_out && counts && ws, "null pointer");
   SVGB_REQUIRE(max_iters >= 1, "max_iters must be >= 1");
+  const long long xhs = x_head_stride ? x_head_stride : static_cast<long long>(N) * D;
+  SVGB_REQUIRE(xhs >= static_cast<long long>(N) * D && xhs % 8 == 0, "x_head_stride %lld invalid (>= N*D, multiple of 8)", xhs);
   size_t need = 0;
   if (svgb_kmeans_bytes(BH, N, K, D, &need)) return -1;
   SVGB_REQUIRE(ws_bytes >= need, "workspace too small: %zu < %zu", ws_bytes, need);
@@ -554,19 +674,18 @@ int svgb_kmeans_run(const void* x, const void* init_centroids, int BH, int N, in
   void* cb1 = w + L.cbuf1;
   KmState* state = reinterpret_cast<KmState*>(w + L.state);
   float* shift = reinterpret_cast<float*>(w + L.state + 64);
-  float* x_sq = reinterpret_cast<float*>(w + L.xsq);
 
   km_init_state_kernel<<<1, 1, 0, st>>>(state, shift);
   SVGB_LAUNCH_OK();
   SVGB_CUDA(cudaMemcpyAsync(cb0, init_centroids, 2ull * BH * K * D, cudaMemcpyDeviceToDevice, st));
-  if (launch_sqnorm(x, x_sq, static_cast<long long>(BH) * N, D, dtype, 1, st)) return -1;
+  // |x|^2 (batch_kmeans_Euclid:704) is computed inside the assign kernel from the X tile it already holds
   for (int it = 0; it < max_iters; ++it) {
     // every kernel of an iteration is a no-op once state->done is set (device-side `break`)
     if (launch_csq(cb0, cb1, csqp, BH, K, D, dtype, state, st)) return -1;
-    if (dispatch_assign(x, cb0, cb1, x_sq, csqp, labels, BH, N, K, D, dtype, state, st)) return -1;
+    if (dispatch_assign(x, xhs, cb0, cb1, nullptr, csqp, labels, BH, N, K, D, dtype, state, st)) return -1;
     if (argsort_labels_impl(labels, BH, N, K, perm, counts, offs, w + L.sort, &state->done, st)) return -1;
     // update reads buffer `cur`, writes the other one
-    if (launch_update(x, perm, counts, offs, cb0, cb1, cb1, cb0, shift, BH, N, K, D, dtype, state, st)) return -1;
+    if (launch_update(x, xhs, perm, counts, offs, cb0, cb1, cb1, cb0, shift, BH, N, K, D, dtype, state, st)) return -1;
     km_commit_kernel<<<1, 1, 0, st>>>(state, shift, tol, it);
     SVGB_LAUNCH_OK();
   }
@@ -574,6 +693,9 @@ int svgb_kmeans_run(const void* x, const void* init_centroids, int BH, int N, in
   km_finalize_kernel<<<64, 256, 0, st>>>(state, static_cast<const uint4*>(cb0), static_cast<const uint4*>(cb1),
                                          static_cast<uint4*>(centroids_out), n_vec, n_iter_out);
   SVGB_LAUNCH_OK();
+  // the member lists the last executed update summed over are the stable argsort of the returned labels
+  if (perm_out)
+    SVGB_CUDA(cudaMemcpyAsync(perm_out, perm, sizeof(int) * static_cast<size_t>(BH) * N, cudaMemcpyDeviceToDevice, st));
   return 0;
 }
 

@@ -329,9 +329,11 @@ def kmeans_update(x, labels, c_old):
     return c_new, counts, shift
 
 
-def kmeans_run(x, init_centroids, max_iters, tol=1e-4):
+def kmeans_run(x, init_centroids, max_iters, tol=1e-4, want_perm=False):
     """Whole Lloyd loop on the device (no host sync).  Returns labels int32 [BH,N], centroids [BH,K,D],
-    counts int32 [BH,K], n_iter int32[1] (device)."""
+    counts int32 [BH,K], n_iter int32[1] (device) and, with want_perm, the stable argsort of the labels int32 [BH,N]
+    (the member lists of the last centroid update).  x may be a view whose heads are further apart than N*D (the video
+    part of a [H, S, D] tensor): it is clustered in place, without a packing copy."""
     _need_cuda(x, init_centroids)
     BH, N, D = x.shape
     K = init_centroids.shape[1]
@@ -340,12 +342,19 @@ def kmeans_run(x, init_centroids, max_iters, tol=1e-4):
     cents = torch.empty(BH, K, D, dtype=x.dtype, device=x.device)
     counts = torch.empty(BH, K, dtype=torch.int32, device=x.device)
     n_iter = torch.zeros(1, dtype=torch.int32, device=x.device)
-    xc, ic = x.contiguous(), init_centroids.contiguous()
-    check(lib().svgb_kmeans_run(xc.data_ptr(), ic.data_ptr(), BH, N, K, D,
-                                _dt(x), int(max_iters), float(tol), labels.data_ptr(), cents.data_ptr(),
-                                counts.data_ptr(), n_iter.data_ptr(), ws.data_ptr(), ws.numel(), _stream(x)),
-          "svgb_kmeans_run")
-    _bump(3 + 7 * int(max_iters))
+    perm = torch.empty(BH, N, dtype=torch.int32, device=x.device) if want_perm else None
+    strided_ok = x.stride(2) == 1 and x.stride(1) == D and (BH == 1 or (x.stride(0) >= N * D and x.stride(0) % 8 == 0))
+    xc = x if strided_ok else x.contiguous()
+    head_stride = xc.stride(0) if BH > 1 else N * D
+    ic = init_centroids.contiguous()
+    check(lib().svgb_kmeans_run_sorted(xc.data_ptr(), head_stride, ic.data_ptr(), BH, N, K, D,
+                                       _dt(x), int(max_iters), float(tol), labels.data_ptr(), cents.data_ptr(),
+                                       counts.data_ptr(), n_iter.data_ptr(), perm.data_ptr() if want_perm else None,
+                                       ws.data_ptr(), ws.numel(), _stream(x)),
+          "svgb_kmeans_run_sorted")
+    _bump(2 + 7 * int(max_iters))
+    if want_perm:
+        return labels, cents, counts, n_iter, perm
     return labels, cents, counts, n_iter
 
 

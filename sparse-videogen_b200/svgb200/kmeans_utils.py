@@ -65,6 +65,18 @@ def batch_kmeans_Euclid(x, n_clusters, max_iters=100, tol=1e-4, init_centroids=N
     return labels.to(torch.int64), cents, counts, LazyInt(n_iter)
 
 
+def batch_kmeans_Euclid_sorted(x, n_clusters, max_iters=100, tol=1e-4, init_centroids=None):
+    """batch_kmeans_Euclid for the SAP cores: same clustering, labels stay int32 and the stable argsort of the labels
+    comes back as a fifth value (the reference recomputes it: permute_tensor_by_labels, svg/kmeans_utils.py:829-838)."""
+    B, N, D = x.shape
+    if init_centroids is None:
+        idx = torch.randint(0, N, (B, n_clusters), device=x.device)  # GPU generator, like :708
+        init_centroids = torch.gather(x, 1, idx[..., None].expand(-1, -1, D))
+    init_centroids = init_centroids.reshape(B, n_clusters, D)
+    labels, cents, counts, n_iter, perm = core.kmeans_run(x, init_centroids, max_iters, tol, want_perm=True)
+    return labels, cents, counts, LazyInt(n_iter), perm
+
+
 def identify_dynamic_map(query_centroids, key_centroids, q_cluster_sizes, k_cluster_sizes, p, min_kc_ratio=0):
     """svg/kmeans_utils.py:864-896 -> bool [B,H,QC,KC]."""
     B, H, QC, D = query_centroids.shape

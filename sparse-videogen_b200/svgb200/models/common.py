@@ -10,7 +10,7 @@ import torch
 
 from .. import core
 from ..timer import time_logging_decorator
-from ..kmeans_utils import batch_kmeans_Euclid
+from ..kmeans_utils import batch_kmeans_Euclid, batch_kmeans_Euclid_sorted
 
 
 def sparsity_to_width(sparsity, context_length, num_frame, frame_size):
@@ -60,17 +60,22 @@ class KMeansState:
         self.q_centroids = {}
         self.k_centroids = {}
 
-    def cluster(self, key, query, kmat, num_q, num_k, iters_init, iters_step):
-        """query/kmat: [BH, N, D].  Returns (qlabels, qcent, qsizes, klabels, kcent, ksizes)."""
+    def cluster(self, key, query, kmat, num_q, num_k, iters_init, iters_step, sorted_members=False):
+        """query/kmat: [BH, N, D] (views with a larger head stride are clustered in place).  Returns (qlabels, qcent,
+        qsizes, klabels, kcent, ksizes); with sorted_members the labels are int32 and the stable argsorts of both label
+        sets are appended (q_perm, k_perm)."""
+        run = batch_kmeans_Euclid_sorted if sorted_members else batch_kmeans_Euclid
         if key not in self.q_centroids:
-            ql, qc, qs, _ = batch_kmeans_Euclid(query, num_q, max_iters=iters_init)
-            kl, kc, ks, _ = batch_kmeans_Euclid(kmat, num_k, max_iters=iters_init)
+            rq = run(query, num_q, max_iters=iters_init)
+            rk = run(kmat, num_k, max_iters=iters_init)
         else:
-            ql, qc, qs, _ = batch_kmeans_Euclid(query, num_q, max_iters=iters_step, init_centroids=self.q_centroids[key])
-            kl, kc, ks, _ = batch_kmeans_Euclid(kmat, num_k, max_iters=iters_step, init_centroids=self.k_centroids[key])
-        self.q_centroids[key] = qc
-        self.k_centroids[key] = kc
-        return ql, qc, qs, kl, kc, ks
+            rq = run(query, num_q, max_iters=iters_step, init_centroids=self.q_centroids[key])
+            rk = run(kmat, num_k, max_iters=iters_step, init_centroids=self.k_centroids[key])
+        self.q_centroids[key] = rq[1]
+        self.k_centroids[key] = rk[1]
+        if sorted_members:
+            return rq[0], rq[1], rq[2], rk[0], rk[1], rk[2], rq[4], rk[4]
+        return rq[0], rq[1], rq[2], rk[0], rk[1], rk[2]
 
 
 class SVG1Core:
@@ -294,11 +299,24 @@ class SAPCore:
         self.state = state if state is not None else KMeansState()
         self.last = {}
 
-    def kmeans_clustering(self, query_video, key_video, layer_idx):
+    def kmeans_clustering(self, query_video, key_video, layer_idx, sorted_members=False):
         BH, N, D = query_video.shape[0] * query_video.shape[1], query_video.shape[2], query_video.shape[3]
-        return self.state.cluster(layer_idx, query_video.reshape(BH, N, D), key_video.reshape(BH, N, D),
+        as3 = (lambda t: t[0]) if query_video.shape[0] == 1 else (lambda t: t.reshape(BH, N, D))  # keep views views
+        return self.state.cluster(layer_idx, as3(query_video), as3(key_video),
                                   self.num_q_centroids, self.num_k_centroids, self.kmeans_iter_init,
-                                  self.kmeans_iter_step)
+                                  self.kmeans_iter_step, sorted_members=sorted_members)
+
+    def _text_constants(self, H, V, S, dev):
+        """Identity order of the text tokens and the (prompt, padding) block sizes; built once per shape (a fresh
+        torch.tensor(..., device=) per call is a synchronous pageable copy)."""
+        key = (H, V, S, str(dev), self.prompt_length)
+        if getattr(self, "_text_key", None) != key:
+            ctx = S - V
+            self._text_tail = torch.arange(V, S, device=dev, dtype=torch.int32).expand(H, ctx)
+            self._text_extra = torch.tensor([self.prompt_length, ctx - self.prompt_length], dtype=torch.int32,
+                                            device=dev).expand(H, 2)
+            self._text_key = key
+        return self._text_tail, self._text_extra
 
     def log_density(self, timestep, layer_idx, dyn_map, q_sizes, k_sizes):
         """One JSON line per sparse call in the reference's schema (hyvideo/attention.py:786-802), read by
@@ -324,28 +342,26 @@ class SAPCore:
         layer_idx = self.layer_idx if layer_idx is None else layer_idx
         ctx, V = self.context_length, self.num_frame * self.frame_size
         dev = query.device
-        qv = query[:, :, :V].contiguous() if ctx else query
-        kv = key[:, :, :V].contiguous() if ctx else key
+        # the video part is clustered in place (a strided view; the reference packs it with .contiguous()), and the
+        # cluster-sorted token order comes back from the last centroid update instead of two more argsort passes
+        qv = query[:, :, :V] if ctx else query
+        kv = key[:, :, :V] if ctx else key
         with time_logging_decorator("Level 3.5 - kmeans clustering"):
-            ql, qc, qs, kl, kc, ks = self.kmeans_clustering(qv, kv, layer_idx)
+            ql, qc, qs, kl, kc, ks, q_perm, k_perm = self.kmeans_clustering(qv, kv, layer_idx, sorted_members=True)
         QC, KC = self.num_q_centroids, self.num_k_centroids
         dyn = identify_dynamic_map(qc.view(cfg, H, QC, D), kc.view(cfg, H, KC, D), qs.view(cfg, H, QC),
                                    ks.view(cfg, H, KC), self.top_p_kmeans, self.min_kc_ratio).view(H, QC, KC)
-        q_perm, _ = core.argsort_labels(ql.view(H, V), QC)
-        k_perm, _ = core.argsort_labels(kl.view(H, V), KC)
         row_sz, col_sz = qs.view(H, QC), ks.view(H, KC)
         if ctx:
             # HunyuanVideo: prompt block <-> everything but the padding, padding <-> itself
             # (dynamic_map_post_processing, hyvideo/attention.py:657-702)
-            unprompt = ctx - self.prompt_length
-            tail = torch.arange(V, S, device=dev, dtype=torch.int32).expand(H, ctx)
+            tail, extra = self._text_constants(H, V, S, dev)
             q_perm = torch.cat([q_perm, tail], dim=1)
             k_perm = torch.cat([k_perm, tail], dim=1)
             dyn = torch.nn.functional.pad(dyn, (0, 2, 0, 2), value=False)
             dyn[:, -2, :-1] = True
             dyn[:, :-1, -2] = True
             dyn[:, -1, -1] = True
-            extra = torch.tensor([self.prompt_length, unprompt], dtype=torch.int32, device=dev).expand(H, 2)
             row_sz = torch.cat([row_sz, extra], dim=1)
             col_sz = torch.cat([col_sz, extra], dim=1)
         with time_logging_decorator("Level 3 - semantic aware permutation"):
@@ -361,6 +377,14 @@ class SAPCore:
             with time_logging_decorator("Level 3 - density calculation and logging"):
                 self.log_density(0 if timestep is None else timestep, layer_idx, dyn, row_sz, col_sz)
         return out
+
+    def sparse_core_head_parallel(self, query, key, value, hp, layer_idx=None, timestep=None, out=None):
+        """SVG2 core on this rank's heads ([1, H_local, S, D], interleaved ownership: global head = i * world + rank),
+        followed by the output all-gather (svgb200.parallel.HeadParallel).  Every SVG2 stage is independent per head
+        (k-means, dynamic map, permutation, attention), so no other exchange is needed; the centroid state of this
+        object covers the local heads only.  Returns [1, H_local * world, S, D]."""
+        o_local = self.sparse_core(query, key, value, layer_idx, timestep)
+        return hp.gather_heads(o_local, out=out)
 
     def attention_core_logic(self, query, key, value, timestep, layer_idx=None, cu_max_seqlens=None):
         cfg, H, S, D = query.shape

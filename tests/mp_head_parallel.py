@@ -36,6 +36,30 @@ def main():
                                                  sampled_rows=rows)
         torch.cuda.synchronize()
         ok = ok and bool(torch.equal(out, ref))
+    # SVG2 core, head-parallel: same centroids as the single-GPU run (the state is pre-seeded with rows of q / k so that
+    # both runs start the Lloyd iterations from identical centroids), gathered output must be bit-identical
+    from svgb200.models import wan
+    from svgb200.models.common import KMeansState
+
+    Fw, Pw = 4, 1500
+    Sw = Fw * Pw
+    qw, kw, vw = (t[:, :, :Sw].contiguous() for t in (q, k, v))
+
+    def seeded_state(qq, kk):
+        st = KMeansState()
+        st.q_centroids[0] = qq[0, :, :48].contiguous()
+        st.k_centroids[0] = kk[0, :, :96].contiguous()
+        return st
+
+    def make(state):
+        return wan.WanSAPCore(Fw, Pw, num_q_centroids=48, num_k_centroids=96, top_p_kmeans=0.8, min_kc_ratio=0.1,
+                              kmeans_iter_init=2, kmeans_iter_step=2, state=state)
+
+    ref2 = make(seeded_state(qw, kw)).sparse_core(qw, kw, vw)
+    ql, kl, vl = (shard_heads(t, world, hp.rank) for t in (qw, kw, vw))
+    out2 = make(seeded_state(ql, kl)).sparse_core_head_parallel(ql, kl, vl, hp)
+    torch.cuda.synchronize()
+    ok = ok and bool(torch.equal(out2, ref2))
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if hp.rank == 0:
