@@ -257,8 +257,8 @@ def _time(fn, warm=2, iters=3):
 
 
 def svg2_pipeline_probe(dev, model):
-    """Whole SVG2 core (k-means x2 -> dynamic map -> argsort x2 -> permute x3 -> plan -> attention with fused inverse
-    permutation) at a model's full shape, on tokens with cluster structure: per-stage CUDA-event times + the total of
+    """Whole SVG2 core (k-means x2, which also returns the cluster-sorted token order -> dynamic map -> permute x3 ->
+    plan -> attention with fused inverse permutation) at a model's full shape, on tokens with cluster structure: per-stage CUDA-event times + the total of
     a warm-started step call (2 Lloyd iterations, the reference's steady state)."""
     from svgb200 import core, kmeans_utils as ku
     from svgb200.models import hyvideo as hy, wan
@@ -284,16 +284,14 @@ def svg2_pipeline_probe(dev, model):
     last = sap.last
     dyn, row_sz, col_sz, q_perm, k_perm = (last[x] for x in ("dynamic_map", "q_sizes", "k_sizes", "q_sorted_indices",
                                                                "k_sorted_indices"))
-    qv = q[:, :, :V].reshape(Hh, V, D).contiguous()
-    kv = k[:, :, :V].reshape(Hh, V, D).contiguous()
+    qv, kv = q[0, :, :V], k[0, :, :V]  # strided views of the video part, clustered in place like sparse_core does
     qc0, kc0 = sap.state.q_centroids[sap.layer_idx], sap.state.k_centroids[sap.layer_idx]
     st = {}
-    st["kmeans_q_2it"] = _time(lambda: ku.batch_kmeans_Euclid(qv, QC, max_iters=2, init_centroids=qc0), 1, 3)
-    st["kmeans_k_2it"] = _time(lambda: ku.batch_kmeans_Euclid(kv, KC, max_iters=2, init_centroids=kc0), 1, 3)
-    ql, qc, qs, _ = ku.batch_kmeans_Euclid(qv, QC, max_iters=2, init_centroids=qc0)
-    kl, kc, ks, _ = ku.batch_kmeans_Euclid(kv, KC, max_iters=2, init_centroids=kc0)
+    st["kmeans_q_2it"] = _time(lambda: ku.batch_kmeans_Euclid_sorted(qv, QC, max_iters=2, init_centroids=qc0), 1, 3)
+    st["kmeans_k_2it"] = _time(lambda: ku.batch_kmeans_Euclid_sorted(kv, KC, max_iters=2, init_centroids=kc0), 1, 3)
+    ql, qc, qs, _, _ = ku.batch_kmeans_Euclid_sorted(qv, QC, max_iters=2, init_centroids=qc0)
+    kl, kc, ks, _, _ = ku.batch_kmeans_Euclid_sorted(kv, KC, max_iters=2, init_centroids=kc0)
     st["dynamic_map"] = _time(lambda: ku.identify_dynamic_map(qc[None], kc[None], qs[None], ks[None], 0.9, 0.1), 1, 3)
-    st["argsort_x2"] = _time(lambda: (core.argsort_labels(ql, QC), core.argsort_labels(kl, KC)), 1, 3)
     st["permute_x3"] = _time(lambda: (core.permute_gather(q, q_perm), core.permute_gather(k, k_perm),
                                       core.permute_gather(v, k_perm)), 1, 3)
     qp, kp, vp = core.permute_gather(q, q_perm), core.permute_gather(k, k_perm), core.permute_gather(v, k_perm)
@@ -303,7 +301,8 @@ def svg2_pipeline_probe(dev, model):
     fl = 4.0 * D * (row_sz.double()[:, :, None] * col_sz.double()[:, None, :] * dyn).sum().item()
     return {"shape": f"H={Hh} S={Sm} QC={QC} KC={KC} top_p=0.9 (k-means on clustered synthetic tokens)",
             "density": fl / (4.0 * D * Hh * Sm * Sm), "step_call_ms": total, "stages_ms": st,
-            "front_half_ms": total - st["attention"], "attention_tflops": fl / st["attention"] / 1e9,
+            "front_half_ms": total - st["attention"], "glue_ms": total - sum(st.values()),
+            "attention_tflops": fl / st["attention"] / 1e9,
             "step_tflops": fl / total / 1e9}
 
 

@@ -14,9 +14,13 @@ namespace svgb {
 //   one CTA per head; thread per q-block walks its map row, merges selected k-blocks that are
 //   adjacent in token space into runs and cuts runs into <=128-column chunks.
 // =============================================================================================
-// Two kernels.  (1) plan_lists_kernel -- grid (ceil(QC/64), BH): thread per q-block walks its map row and writes
-// the chunk (or run) list; (2) plan_items_kernel -- one CTA per head: work items from the row sizes and list lengths.
-__global__ void __launch_bounds__(64)
+// Two kernels.  (1) plan_lists_kernel -- grid (ceil(QC/8), BH), one WARP per q-block: the map row is read with
+// coalesced byte loads 32 columns at a time, a ballot gives the selected non-empty k-blocks, the (warp-uniform) run
+// walk visits only the set bits and the chunks of a finished run are written by the lanes in parallel;
+// (2) plan_items_kernel -- one CTA per head: work items from the row sizes and list lengths.
+// (The first version walked each row byte by byte with one thread: 0.37 ms at 24 x 400 x 1000; this one ~0.02 ms.)
+constexpr int kPlanWarps = 8;
+__global__ void __launch_bounds__(kPlanWarps * 32)
 plan_lists_kernel(const uint8_t* __restrict__ map, const int* __restrict__ row_sz, const int* __restrict__ col_sz,
                   int QC, int KC, int chunk_cap, int gather, int2* __restrict__ chunks, int* __restrict__ nch_of,
                   int* __restrict__ tot_of) {
@@ -24,70 +28,83 @@ plan_lists_kernel(const uint8_t* __restrict__ map, const int* __restrict__ row_s
   // gathers exactly-full 128-key chunks across run boundaries.
   extern __shared__ int sm[];
   int* coloff = sm;  // KC + 1
+  __shared__ int wsum[kPlanWarps];
   const int bh = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   row_sz += static_cast<size_t>(bh) * QC;
   col_sz += static_cast<size_t>(bh) * KC;
-  // exclusive prefix sum of the key-block sizes: per-thread partial sums over a contiguous slice, then a serial
-  // pass over the 64 partials
-  __shared__ int part[64];
-  const int per = (KC + 63) / 64;
+  // exclusive prefix sum of the key-block sizes: a contiguous slice per thread, warp scan, serial pass over 8 warp sums
   {
+    const int nthr = kPlanWarps * 32;
+    const int per = (KC + nthr - 1) / nthr;
+    const int j0 = min(KC, static_cast<int>(threadIdx.x) * per), j1 = min(KC, j0 + per);
     int acc = 0;
-    for (int j = threadIdx.x * per; j < min(KC, (static_cast<int>(threadIdx.x) + 1) * per); ++j) acc += col_sz[j];
-    part[threadIdx.x] = acc;
-  }
-  __syncthreads();
-  {
-    int base = 0;
-    for (int t = 0; t < static_cast<int>(threadIdx.x); ++t) base += part[t];
-    for (int j = threadIdx.x * per; j < min(KC, (static_cast<int>(threadIdx.x) + 1) * per); ++j) {
+    for (int j = j0; j < j1; ++j) acc += col_sz[j];
+    int incl = acc;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int n = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += n;
+    }
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    int base = incl - acc;
+    for (int w = 0; w < warp; ++w) base += wsum[w];
+    for (int j = j0; j < j1; ++j) {
       coloff[j] = base;
       base += col_sz[j];
     }
-    if (threadIdx.x == 63) coloff[KC] = base;
+    if (threadIdx.x == nthr - 1) coloff[KC] = base;  // the last thread's slice ends at KC (possibly empty)
   }
   __syncthreads();
-  const int qb = blockIdx.x * 64 + threadIdx.x;
+  const int qb = blockIdx.x * kPlanWarps + warp;
   if (qb >= QC) return;
   const size_t list = (static_cast<size_t>(bh) * QC + qb) * chunk_cap;
   int2* out = chunks + list;
   const uint8_t* mrow = map + (static_cast<size_t>(bh) * QC + qb) * KC;
-  int n = 0, total = 0;
+  int n = 0, total = 0;  // warp-uniform
   if (row_sz[qb] > 0) {
     int run_s = -1, run_e = -1;
-    for (int j = 0; j <= KC; ++j) {
-      bool sel = false;
-      int s = 0, e = 0;
-      if (j < KC) {
-        s = coloff[j];
-        e = coloff[j + 1];
-        sel = (mrow[j] != 0) && (e > s);
-      }
-      if (sel && run_s >= 0 && s == run_e) {
-        run_e = e;  // contiguous in token space: extend
-        continue;
-      }
-      if (run_s >= 0 && (sel || j == KC)) {
-        if (gather) {
-          if (n < chunk_cap - 1) out[n++] = make_int2(run_s, total);
-          total += run_e - run_s;
-        } else {
-          for (int p = run_s; p < run_e && n < chunk_cap; p += kChunkCols) {
-            const int valid = min(kChunkCols, run_e - p);
-            out[n++] = make_int2(p, chunk_meta(valid, false));
-          }
+    auto flush = [&]() {
+      if (gather) {
+        if (n < chunk_cap - 1) {
+          if (lane == 0) out[n] = make_int2(run_s, total);
+          ++n;
         }
-        run_s = -1;
+        total += run_e - run_s;
+      } else {
+        const int cnt = min((run_e - run_s + kChunkCols - 1) / kChunkCols, chunk_cap - n);
+        for (int c = lane; c < cnt; c += 32) {
+          const int p = run_s + c * kChunkCols;
+          out[n + c] = make_int2(p, chunk_meta(min(kChunkCols, run_e - p), false));
+        }
+        n += cnt;
       }
-      if (sel) {
-        run_s = s;
-        run_e = e;
+    };
+    for (int j0 = 0; j0 < KC; j0 += 32) {
+      const int j = j0 + lane;
+      const bool sel = j < KC && mrow[j] != 0 && coloff[j + 1] > coloff[j];
+      unsigned m = __ballot_sync(0xffffffffu, sel);
+      while (m) {
+        const int jj = j0 + __ffs(m) - 1;
+        m &= m - 1;
+        const int s = coloff[jj], e = coloff[jj + 1];
+        if (run_s >= 0 && s == run_e) {
+          run_e = e;  // contiguous in token space (only empty k-blocks in between): extend
+        } else {
+          if (run_s >= 0) flush();
+          run_s = s;
+          run_e = e;
+        }
       }
     }
-    if (gather) out[n] = make_int2(0, total);  // sentinel: ends the last run
+    if (run_s >= 0) flush();
+    if (gather && lane == 0) out[n] = make_int2(0, total);  // sentinel: ends the last run
   }
-  nch_of[static_cast<size_t>(bh) * QC + qb] = n;
-  tot_of[static_cast<size_t>(bh) * QC + qb] = total;
+  if (lane == 0) {
+    nch_of[static_cast<size_t>(bh) * QC + qb] = n;
+    tot_of[static_cast<size_t>(bh) * QC + qb] = total;
+  }
 }
 
 __global__ void plan_items_kernel(const int* __restrict__ row_sz, const int* __restrict__ nch_all,
@@ -113,7 +130,11 @@ __global__ void plan_items_kernel(const int* __restrict__ row_sz, const int* __r
   const int bh = blockIdx.x;
   row_sz += static_cast<size_t>(bh) * QC;
   const bool pair = !gather && pair_tails;
-  for (int i = threadIdx.x; i < QC; i += blockDim.x) nch_of[i] = nch_all[static_cast<size_t>(bh) * QC + i];
+  for (int i = threadIdx.x; i < QC; i += blockDim.x) {
+    nch_of[i] = nch_all[static_cast<size_t>(bh) * QC + i];
+    rowoff[i] = row_sz[i];  // staged: the serial pass below turns the sizes into offsets in place
+  }
+  __syncthreads();
   // split of the last r % 256 rows of a q-block (pair == true):
   //   rem <= short                : short tail
   //   short < rem <= 128          : long tail
@@ -122,9 +143,9 @@ __global__ void plan_items_kernel(const int* __restrict__ row_sz, const int* __r
   if (threadIdx.x == 32) {
     int acc = 0, it = 0, nl = 0, ns = 0;
     for (int i = 0; i < QC; ++i) {
+      const int r = rowoff[i];
       rowoff[i] = acc;
       itembase[i] = it;
-      const int r = row_sz[i];
       acc += r;
       const int rem = r % kItemRows;
       int lg = 0, sh = 0, n2 = (r + kItemRows - 1) / kItemRows;
@@ -582,7 +603,7 @@ static int plan_varblock_impl(const uint8_t* map, const int32_t* row_sz, const i
   // SVGB_ATTN_PAIR=0 keeps every tail a single-tile item (A/B switch for bring-up)
   static const int pair_tails = [] { const char* e = getenv("SVGB_ATTN_PAIR"); return (e && e[0] == '0') ? 0 : 1; }();
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  plan_lists_kernel<<<dim3((QC + 63) / 64, BH), 64, smem1, st>>>(map, row_sz, col_sz, QC, KC, cap, gather ? 1 : 0,
+  plan_lists_kernel<<<dim3((QC + kPlanWarps - 1) / kPlanWarps, BH), kPlanWarps * 32, smem1, st>>>(map, row_sz, col_sz, QC, KC, cap, gather ? 1 : 0,
                                                                  reinterpret_cast<int2*>(ws + plan->chunks_off), nch_of, tot_of);
   SVGB_LAUNCH_OK();
   // SVGB_ATTN_TAIL=0 keeps short tails in the main kernel's dual items (A/B switch for bring-up)

@@ -4,7 +4,7 @@
 // Every rounding the reference's torch ops perform on 16-bit tensors is reproduced:
 //   scores = round16(round16(qc . kc) / float(sqrt(D)))          (matmul then `/`, :877)
 //   prob   = round16(w * exp(s - max) / max(sum, 1e-12))         (weighted_softmax, :852-861, fp32 inside)
-//   sort descending; ties -> lower column first (the reference's torch.sort is unstable; we pin it)
+//   sort descending (stable radix sort); ties -> lower column first (the reference's torch.sort is unstable; we pin it)
 //   cums   = torch.cumsum of the sorted 16-bit tensor AS THE CUDA BACKEND COMPUTES IT (the reference runs on the
 //            GPU): blocks of 2*nx elements scanned by a Sklansky network in which every add rounds to 16 bit, block
 //            totals carried into element 0 of the next block (ATen/native/cuda/ScanUtils.cuh:
@@ -46,10 +46,10 @@ __device__ __forceinline__ float block_reduce(float v, float* red, bool is_max) 
   return r;
 }
 
-// q-centroid rows per CTA (they share every key-centroid row read).  Measured at 24 x 400 x 1000 (ncu,
-// profiles/r02_dynmap_ncu_summary.json): the kernel is INSTRUCTION-bound (1.06e9 warp instructions, issue slots 71 % busy,
-// L2 0.6 %): ~85 % of them are the 55-pass bitonic sort, the scan and the scatter of each row, so sharing the key reads
-// among 8 rows (1.53 ms) loses to one row per CTA (1.28 ms), which keeps 8 CTAs per SM resident.
+// q-centroid rows per CTA (they share every key-centroid row read).  Measured at 24 x 400 x 1000 with the first
+// (bitonic-sort) version (ncu, profiles/r02_dynmap_ncu_summary.json): the kernel is INSTRUCTION-bound (1.06e9 warp
+// instructions, issue slots 71 % busy, L2 0.6 %), so sharing the key reads among 8 rows (1.53 ms) lost to one row per
+// CTA (1.28 ms), which keeps 8 CTAs per SM resident.  The sort is now a two-pass radix sort (see below).
 constexpr int kDynRows = 1;
 
 template <bool BF16>
@@ -61,7 +61,8 @@ dynmap_kernel(const uint16_t* __restrict__ qc, const uint16_t* __restrict__ kc, 
   float* sc_all = reinterpret_cast<float*>(keys + KCpad);    // kDynRows x KCpad : scores, then weighted exps / cums
   float* qrows = sc_all + kDynRows * KCpad;                  // kDynRows x D
   float* red = qrows + kDynRows * D;                         // 32
-  uint8_t* keep = reinterpret_cast<uint8_t*>(red + 32);      // KCpad
+  int* rhist = reinterpret_cast<int*>(red + 32);             // 8 warps x 256 radix bins
+  uint8_t* keep = reinterpret_cast<uint8_t*>(rhist + 8 * 256);  // KCpad
   const int i0 = blockIdx.x * kDynRows, bh = blockIdx.y;
   const int nr = min(kDynRows, QC - i0);
   for (int e = threadIdx.x; e < kDynRows * D; e += blockDim.x) {
@@ -141,19 +142,66 @@ dynmap_kernel(const uint16_t* __restrict__ qc, const uint16_t* __restrict__ kc, 
     keys[j] = key;
   }
   __syncthreads();
-  // bitonic sort, descending
-  for (int k = 2; k <= KCpad; k <<= 1) {
-    for (int jj = k >> 1; jj > 0; jj >>= 1) {
-      for (int t = threadIdx.x; t < KCpad; t += blockDim.x) {
-        const int p = t ^ jj;
-        if (p > t) {
-          const uint32_t a = keys[t], b = keys[p];
-          const bool desc = (t & k) == 0;
-          if (desc ? (a < b) : (a > b)) {
-            keys[t] = b;
-            keys[p] = a;
-          }
+  // Stable LSD radix sort (two 8-bit passes) on the 16-bit probability, descending; equal probabilities keep ascending
+  // column order because the input is in column order and both passes are stable.  Each warp owns a contiguous segment,
+  // counts / places 32 elements per step with match_any ranks, the (digit, warp) table is scanned once per pass.
+  // keys -> alt (low byte) -> keys (high byte).  ~25x fewer instructions than the 55-pass bitonic network it replaces.
+  {
+    uint32_t* alt = reinterpret_cast<uint32_t*>(sc);  // free between the softmax and the scan
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int seg = ((KC + nwarps - 1) / nwarps + 31) & ~31;
+    const int e0 = warp * seg, e1 = min(KC, e0 + seg);
+    const unsigned lt = (1u << lane) - 1u;
+    for (int pass = 0; pass < 2; ++pass) {
+      const uint32_t* src = pass == 0 ? keys : alt;
+      uint32_t* dst = pass == 0 ? alt : keys;
+      const int shift = pass * 8;
+      for (int x = threadIdx.x; x < nwarps * 256; x += blockDim.x) rhist[x] = 0;
+      __syncthreads();
+      int* mine = rhist + warp * 256;
+      for (int e = e0 + lane; e - lane < e1; e += 32) {
+        const bool valid = e < e1;
+        const int digit = valid ? static_cast<int>(((0xFFFFu - (src[e] >> 16)) >> shift) & 0xFFu) : 256 + lane;
+        const unsigned peers = __match_any_sync(0xffffffffu, digit);
+        if (valid && (peers & lt) == 0) mine[digit] += __popc(peers);
+        __syncwarp();
+      }
+      __syncthreads();
+      {  // thread d: exclusive prefix over the warps for digit d, then a block-wide exclusive scan over the digit totals
+        const int d = threadIdx.x;  // blockDim.x == 256
+        int tot = 0;
+        for (int w = 0; w < nwarps; ++w) {
+          const int v = rhist[w * 256 + d];
+          rhist[w * 256 + d] = tot;
+          tot += v;
         }
+        int incl = tot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int n = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += n;
+        }
+        __shared__ int wtot[8];
+        if (lane == 31) wtot[warp] = incl;
+        __syncthreads();
+        int basew = 0;
+        for (int w = 0; w < warp; ++w) basew += wtot[w];
+        const int excl = basew + incl - tot;
+        for (int w = 0; w < nwarps; ++w) rhist[w * 256 + d] += excl;
+      }
+      __syncthreads();
+      for (int e = e0 + lane; e - lane < e1; e += 32) {
+        const bool valid = e < e1;
+        const uint32_t key = valid ? src[e] : 0u;
+        const int digit = valid ? static_cast<int>(((0xFFFFu - (key >> 16)) >> shift) & 0xFFu) : 256 + lane;
+        const unsigned peers = __match_any_sync(0xffffffffu, digit);
+        const int rank = __popc(peers & lt);
+        int pos = 0;
+        if (valid) pos = mine[digit] + rank;
+        __syncwarp();
+        if (valid && rank == 0) mine[digit] += __popc(peers);
+        __syncwarp();
+        if (valid) dst[pos] = key;
       }
       __syncthreads();
     }
@@ -238,7 +286,7 @@ extern "C" int svgb_dynamic_map(const void* qc, const void* kc, const int32_t* k
   while ((1ull << ly) < static_cast<unsigned long long>(BH) * QC) ++ly;
   uint32_t log_nx = (9u + lx - ly) / 2u;
   log_nx = log_nx < 4u ? 4u : (log_nx > 9u ? 9u : log_nx);
-  const size_t smem = sizeof(uint32_t) * KCpad + sizeof(float) * (kDynRows * (KCpad + D) + 32) + KCpad +
+  const size_t smem = sizeof(uint32_t) * KCpad + sizeof(float) * (kDynRows * (KCpad + D) + 32) + 8 * 256 * sizeof(int) + KCpad +
                       (log_nx == 4 ? 0 : sizeof(float) * (2u << log_nx) + 16);
   SVGB_REQUIRE(smem <= 200 * 1024, "KC too large for the dynamic-map kernel (%zu B smem)", smem);
   dim3 grid((QC + kDynRows - 1) / kDynRows, BH);

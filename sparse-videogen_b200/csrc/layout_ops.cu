@@ -130,37 +130,78 @@ __global__ void sort_hist_kernel(const int* __restrict__ labels, int S, int K, i
   for (int k = threadIdx.x; k < K; k += blockDim.x) dst[k] = sh[k];
 }
 
-__global__ void sort_scan_kernel(int K, int n_chunks, int* __restrict__ hist, int* __restrict__ counts,
-                                 int* __restrict__ offs, const int* __restrict__ skip) {
+// one CTA per head, one thread per cluster (blockDim.x >= K is not required: clusters are strided): the column scan over
+// the chunks keeps 8 independent loads in flight per thread, then a block-wide exclusive scan over the K totals gives
+// the cluster offsets.  hist is left holding, per (chunk, cluster), the number of that cluster's tokens in EARLIER
+// chunks; the place kernel adds the cluster offset itself (one pass over the table instead of two).
+__global__ void __launch_bounds__(1024)
+sort_scan_kernel(int K, int n_chunks, int* __restrict__ hist, int* __restrict__ counts,
+                 int* __restrict__ offs, const int* __restrict__ skip) {
   extern __shared__ int sh[];  // K totals -> exclusive offsets
+  __shared__ int warp_tot[32];
+  __shared__ int carry_s;
   if (skip && *skip) return;
   const int h = blockIdx.x;
   int* base = hist + static_cast<long long>(h) * n_chunks * K;
   for (int k = threadIdx.x; k < K; k += blockDim.x) {
     int acc = 0;
-    for (int c = 0; c < n_chunks; ++c) {
+    int c = 0;
+    for (; c + 8 <= n_chunks; c += 8) {
+      int v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = base[static_cast<long long>(c + u) * K + k];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        base[static_cast<long long>(c + u) * K + k] = acc;  // tokens of cluster k in earlier chunks
+        acc += v[u];
+      }
+    }
+    for (; c < n_chunks; ++c) {
       const int v = base[static_cast<long long>(c) * K + k];
-      base[static_cast<long long>(c) * K + k] = acc;  // tokens of cluster k in earlier chunks
+      base[static_cast<long long>(c) * K + k] = acc;
       acc += v;
     }
     sh[k] = acc;
     if (counts) counts[static_cast<long long>(h) * K + k] = acc;
   }
+  if (threadIdx.x == 0) carry_s = 0;
   __syncthreads();
-  if (threadIdx.x == 0) {
-    int acc = 0;
-    for (int k = 0; k < K; ++k) {
-      const int v = sh[k];
-      sh[k] = acc;
-      acc += v;
+  // exclusive scan of sh[0..K) in tiles of blockDim.x
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (int k0 = 0; k0 < K; k0 += blockDim.x) {
+    const int k = k0 + threadIdx.x;
+    const int v = k < K ? sh[k] : 0;
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int n = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += n;
     }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      const int t = lane < nwarps ? warp_tot[lane] : 0;
+      int ti = t;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int n = __shfl_up_sync(0xffffffffu, ti, o);
+        if (lane >= o) ti += n;
+      }
+      warp_tot[lane] = ti - t;  // exclusive over warps
+    }
+    __syncthreads();
+    const int excl = carry_s + warp_tot[warp] + incl - v;
+    if (k < K) {
+      sh[k] = excl;
+      if (offs) offs[static_cast<long long>(h) * K + k] = excl;
+    }
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) carry_s = excl + v;
+    __syncthreads();
   }
-  __syncthreads();
-  for (int k = threadIdx.x; k < K; k += blockDim.x) {
-    const int off = sh[k];
-    if (offs) offs[static_cast<long long>(h) * K + k] = off;
-    for (int c = 0; c < n_chunks; ++c) base[static_cast<long long>(c) * K + k] += off;
-  }
+  // the place kernel needs the offsets even when the caller passed offs == nullptr: keep them behind the table
+  int* offs_ws = hist + static_cast<long long>(gridDim.x) * n_chunks * K + static_cast<long long>(h) * K;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) offs_ws[k] = sh[k];
 }
 
 __global__ void __launch_bounds__(32)
@@ -170,7 +211,8 @@ sort_place_kernel(const int* __restrict__ labels, int S, int K, int n_chunks,
   if (skip && *skip) return;
   const int h = blockIdx.y, c = blockIdx.x, lane = threadIdx.x;
   const int* base = hist + (static_cast<long long>(h) * n_chunks + c) * K;
-  for (int k = lane; k < K; k += 32) cnt[k] = base[k];
+  const int* offs_ws = hist + static_cast<long long>(gridDim.y) * n_chunks * K + static_cast<long long>(h) * K;
+  for (int k = lane; k < K; k += 32) cnt[k] = base[k] + offs_ws[k];
   __syncwarp();
   const int s0 = c * kSortChunk, s1 = min(S, s0 + kSortChunk);
   for (int s = s0; s < s1; s += 32) {
@@ -204,7 +246,8 @@ int argsort_labels_impl(const int* labels, int BH, int S, int K, int* perm, int*
   int* hist = static_cast<int*>(ws);
   sort_hist_kernel<<<dim3(n_chunks, BH), 256, K * sizeof(int), st>>>(labels, S, K, n_chunks, hist, skip_flag);
   SVGB_LAUNCH_OK();
-  sort_scan_kernel<<<BH, 256, K * sizeof(int), st>>>(K, n_chunks, hist, counts, offs, skip_flag);
+  const int scan_threads = K >= 1024 ? 1024 : ((K + 31) / 32) * 32;
+  sort_scan_kernel<<<BH, scan_threads, K * sizeof(int), st>>>(K, n_chunks, hist, counts, offs, skip_flag);
   SVGB_LAUNCH_OK();
   sort_place_kernel<<<dim3(n_chunks, BH), 32, K * sizeof(int), st>>>(labels, S, K, n_chunks, hist, perm, skip_flag);
   SVGB_LAUNCH_OK();
@@ -265,7 +308,7 @@ int svgb_head_placement(const void* const* in, void* const* out, int n_tensors,
 int svgb_argsort_labels_bytes(int BH, int S, int K, size_t* bytes) {
   SVGB_REQUIRE(BH > 0 && S > 0 && K > 0 && bytes, "bad arguments");
   const size_t n_chunks = (S + kSortChunk - 1) / kSortChunk;
-  *bytes = align_up(sizeof(int) * BH * n_chunks * K, 256);
+  *bytes = align_up(sizeof(int) * (BH * n_chunks * K + static_cast<size_t>(BH) * K), 256);  // table + cluster offsets
   return 0;
 }
 
