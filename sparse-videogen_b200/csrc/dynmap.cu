@@ -51,8 +51,9 @@ __device__ __forceinline__ float block_reduce(float v, float* red, bool is_max) 
 // instructions, issue slots 71 % busy, L2 0.6 %), so sharing the key reads among 8 rows (1.53 ms) lost to one row per
 // CTA (1.28 ms), which keeps 8 CTAs per SM resident.  The sort is now a two-pass radix sort (see below).
 constexpr int kDynRows = 1;
+static_assert(kDynRows == 1, "the tensor-core score stage puts one q row into the A fragment");
 
-template <bool BF16>
+template <bool BF16, int NBLK>
 __global__ void __launch_bounds__(256)
 dynmap_kernel(const uint16_t* __restrict__ qc, const uint16_t* __restrict__ kc, const int* __restrict__ k_sizes,
               int QC, int KC, int KCpad, int D, float top_p, int preserve, int log_nx, uint8_t* __restrict__ map) {
@@ -71,51 +72,60 @@ dynmap_kernel(const uint16_t* __restrict__ qc, const uint16_t* __restrict__ kc, 
   }
   __syncthreads();
   const float sqrt_d = static_cast<float>(sqrt(static_cast<double>(D)));
-  // Scores of kDynRows q-centroids against every key centroid: one warp per key-centroid row (a coalesced 2*D-byte
-  // read, lanes stride the row in 32-bit pairs), kDynRows dot products per row read, fixed-order butterfly reduction
-  // (deterministic; the summation order of one dot product depends neither on the unrolling nor on kDynRows).
-  // U key rows are in flight per warp (with one row per iteration the phase waited on two dependent L2 loads).
+  // Scores of the q-centroid against every key centroid on the (legacy) warp-level tensor cores: one
+  // mma.sync.m16n8k16 covers 8 key rows x 16 dims with the q row in row 0 of the A fragment (rows 1-15 are zero -- the
+  // op is 2.5 GFLOP in total, what matters is the instruction count: the first version spent ~45 warp instructions per
+  // key row on FMAs and a 5-step shuffle reduction, this one ~4).  Each lane reads 16 contiguous bytes of "its" key row
+  // per 32-dim block (lane = 4 * key + quarter) and feeds them as the B fragments of two k-steps; the q fragment uses
+  // the same dim -> k-slot assignment, so the product is the plain dot product with a hardware-defined fp32 summation
+  // order (deterministic; the 16-bit roundings that follow are the reference's).
   {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    constexpr int U = kDynRows == 1 ? 4 : 2;  // key rows in flight per warp
-    const int nw = D / 64;  // 32-bit words per lane and row (D <= 256)
-    float2 qv[kDynRows][2];  // this lane's q values (D <= 128 keeps them in registers; D = 192 / 256 re-read smem)
+    const int g = lane >> 2, tq = lane & 3;
+    constexpr int nblk = NBLK;  // D / 32, D in {64, 128, 192, 256}
+    uint32_t qa[NBLK][4];       // q fragment: [32-dim block][a0, a2 of the two k-steps]; zero outside lanes 0-3
 #pragma unroll
-    for (int r = 0; r < kDynRows; ++r)
+    for (int sb = 0; sb < NBLK; ++sb)
 #pragma unroll
-      for (int x = 0; x < 2; ++x)
-        qv[r][x] = x < nw ? make_float2(qrows[r * D + 2 * (lane + 32 * x)], qrows[r * D + 2 * (lane + 32 * x) + 1])
-                          : make_float2(0.f, 0.f);
-    for (int j0 = warp * U; j0 < KC; j0 += nwarps * U) {
-      uint32_t w[U][4];
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int j = min(j0 + u, KC - 1);
-        const uint32_t* kr = reinterpret_cast<const uint32_t*>(kc + (static_cast<size_t>(bh) * KC + j) * D);
-#pragma unroll
-        for (int x = 0; x < 4; ++x)
-          if (x < nw) w[u][x] = __ldg(kr + lane + 32 * x);
+      for (int x = 0; x < 4; ++x) {
+        uint32_t v = 0;
+        if (g == 0) {
+          const int d = 32 * sb + 8 * tq + 2 * x;
+          v = static_cast<uint32_t>(f2h<BF16>(qrows[d])) | (static_cast<uint32_t>(f2h<BF16>(qrows[d + 1])) << 16);
+        }
+        qa[sb][x] = v;
       }
+    const int ngroups = (KC + 7) / 8;
+    for (int grp = warp; grp < ngroups; grp += nwarps) {
+      const int j = min(grp * 8 + g, KC - 1);
+      const uint4* kr = reinterpret_cast<const uint4*>(kc + (static_cast<size_t>(bh) * KC + j) * D) + tq;
+      uint4 kb[NBLK];
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
+      for (int sb = 0; sb < NBLK; ++sb) kb[sb] = __ldg(kr + 4 * sb);
+      float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f;
 #pragma unroll
-        for (int r = 0; r < kDynRows; ++r) {
-          float a = 0.f;
-#pragma unroll
-          for (int x = 0; x < 4; ++x)
-            if (x < nw) {
-              const int d2 = lane + 32 * x;
-              const float q0 = x < 2 ? qv[r][x & 1].x : qrows[r * D + 2 * d2];
-              const float q1 = x < 2 ? qv[r][x & 1].y : qrows[r * D + 2 * d2 + 1];
-              a = fmaf(q0, h2f<BF16>(static_cast<uint16_t>(w[u][x] & 0xffff)), a);
-              a = fmaf(q1, h2f<BF16>(static_cast<uint16_t>(w[u][x] >> 16)), a);
-            }
-          for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-          if (lane == 0 && j0 + u < KC) {
-            const float m = h2f<BF16>(f2h<BF16>(a));
-            sc_all[r * KCpad + j0 + u] = h2f<BF16>(f2h<BF16>(m / sqrt_d));
+      for (int sb = 0; sb < NBLK; ++sb) {
+          const uint32_t z = 0u;
+          if constexpr (BF16) {
+            asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                         : "+f"(c0), "+f"(c1), "+f"(c2), "+f"(c3)
+                         : "r"(qa[sb][0]), "r"(z), "r"(qa[sb][1]), "r"(z), "r"(kb[sb].x), "r"(kb[sb].y));
+            asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                         : "+f"(c0), "+f"(c1), "+f"(c2), "+f"(c3)
+                         : "r"(qa[sb][2]), "r"(z), "r"(qa[sb][3]), "r"(z), "r"(kb[sb].z), "r"(kb[sb].w));
+          } else {
+            asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                         : "+f"(c0), "+f"(c1), "+f"(c2), "+f"(c3)
+                         : "r"(qa[sb][0]), "r"(z), "r"(qa[sb][1]), "r"(z), "r"(kb[sb].x), "r"(kb[sb].y));
+            asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                         : "+f"(c0), "+f"(c1), "+f"(c2), "+f"(c3)
+                         : "r"(qa[sb][2]), "r"(z), "r"(qa[sb][3]), "r"(z), "r"(kb[sb].z), "r"(kb[sb].w));
           }
         }
+      if (g == 0) {  // row 0 of the accumulator tile: lanes 0-3 hold the scores of keys 2*tq, 2*tq + 1 of the group
+        const int jo = grp * 8 + 2 * tq;
+        if (jo < KC) sc_all[jo] = h2f<BF16>(f2h<BF16>(h2f<BF16>(f2h<BF16>(c0)) / sqrt_d));
+        if (jo + 1 < KC) sc_all[jo + 1] = h2f<BF16>(f2h<BF16>(h2f<BF16>(f2h<BF16>(c1)) / sqrt_d));
       }
     }
   }
@@ -277,6 +287,7 @@ extern "C" int svgb_dynamic_map(const void* qc, const void* kc, const int32_t* k
   SVGB_REQUIRE(qc && kc && k_sizes && map, "null pointer");
   SVGB_REQUIRE(BH > 0 && QC > 0 && KC > 0 && KC <= 4096 && D > 0 && D % 64 == 0 && D <= 256, "bad sizes (KC <= 4096, D in {64,128,192,256})");
   SVGB_REQUIRE(dtype == SVGB_BF16 || dtype == SVGB_F16, "dtype %d unsupported", dtype);
+  SVGB_REQUIRE(reinterpret_cast<uintptr_t>(kc) % 16 == 0, "kc must be 16-byte aligned");
   int KCpad = 2;
   while (KCpad < KC) KCpad <<= 1;
   // block size of torch's CUDA scan for a [BH*QC, KC] tensor: get_log_num_threads_x_inner_scan (ScanUtils.cuh:19-41,
@@ -291,15 +302,21 @@ extern "C" int svgb_dynamic_map(const void* qc, const void* kc, const int32_t* k
   SVGB_REQUIRE(smem <= 200 * 1024, "KC too large for the dynamic-map kernel (%zu B smem)", smem);
   dim3 grid((QC + kDynRows - 1) / kDynRows, BH);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (dtype == SVGB_BF16) {
-    SVGB_CUDA(cudaFuncSetAttribute(dynmap_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dynmap_kernel<true><<<grid, 256, smem, st>>>(static_cast<const uint16_t*>(qc), static_cast<const uint16_t*>(kc),
-                                                 k_sizes, QC, KC, KCpad, D, top_p, preserve, static_cast<int>(log_nx), map);
-  } else {
-    SVGB_CUDA(cudaFuncSetAttribute(dynmap_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dynmap_kernel<false><<<grid, 256, smem, st>>>(static_cast<const uint16_t*>(qc), static_cast<const uint16_t*>(kc),
-                                                  k_sizes, QC, KC, KCpad, D, top_p, preserve, static_cast<int>(log_nx), map);
+  auto launch = [&](auto kern) -> int {
+    SVGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    kern<<<grid, 256, smem, st>>>(static_cast<const uint16_t*>(qc), static_cast<const uint16_t*>(kc), k_sizes, QC, KC,
+                                  KCpad, D, top_p, preserve, static_cast<int>(log_nx), map);
+    return 0;
+  };
+  const bool bf = dtype == SVGB_BF16;
+  int rc = 0;
+  switch (D / 32) {
+    case 2: rc = bf ? launch(dynmap_kernel<true, 2>) : launch(dynmap_kernel<false, 2>); break;
+    case 4: rc = bf ? launch(dynmap_kernel<true, 4>) : launch(dynmap_kernel<false, 4>); break;
+    case 6: rc = bf ? launch(dynmap_kernel<true, 6>) : launch(dynmap_kernel<false, 6>); break;
+    default: rc = bf ? launch(dynmap_kernel<true, 8>) : launch(dynmap_kernel<false, 8>); break;
   }
+  if (rc) return rc;
   SVGB_LAUNCH_OK();
   return 0;
 }

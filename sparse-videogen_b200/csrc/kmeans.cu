@@ -61,12 +61,23 @@ struct KmState {  // device-resident loop state
   float shift;
 };
 
+// experiment switches (tools/kmeans_ab.sh builds variants; the defaults are the product configuration)
+#ifndef SVGB_KM_STAGES
+#define SVGB_KM_STAGES 3
+#endif
+#ifndef SVGB_KM_PREFETCH
+#define SVGB_KM_PREFETCH 1
+#endif
+#ifndef SVGB_KM_EPI
+#define SVGB_KM_EPI 0  // 1: accumulators are loaded but not reduced; 2: not even loaded (timing decomposition only)
+#endif
+
 template <int D>
 struct AssignCfg {
   static constexpr int kHalves = D / 64;
   static constexpr int kPanelBytes = 128 * 128;
   static constexpr int kTileBytes = kPanelBytes * kHalves;   // 128 rows x D
-  static constexpr int kStages = 3;                          // centroid ring (128 centroids per stage)
+  static constexpr int kStages = SVGB_KM_STAGES;              // centroid ring (128 centroids per stage)
   static constexpr int kXBytes = 2 * kTileBytes;             // one work item = 256 points
   static constexpr int kRingBytes = kStages * kTileBytes;
   static constexpr int kBarBytes = 256;
@@ -82,6 +93,13 @@ struct AssignBars {
   uint32_t tmem_base;
 };
 static_assert(sizeof(AssignBars) <= 256, "barrier block");
+
+// (bits(d) & mask) | idx in ONE LOP3 (mask in a register, idx an immediate; nvcc emits two for the C expression)
+__device__ __forceinline__ uint32_t pack_idx(float d, int idx, uint32_t mask) {
+  uint32_t r;
+  asm("lop3.b32 %0, %1, %2, %3, 0xEC;" : "=r"(r) : "r"(__float_as_uint(d)), "r"(idx), "r"(mask));
+  return r;
+}
 
 __device__ __forceinline__ float fmin3(float a, float b, float c) {
   float r;
@@ -126,10 +144,10 @@ __device__ __forceinline__ float row_sqnorm_smem(const uint8_t* tile, int r) {
 // centroid ring, the TMEM double buffers and their barrier phases run on one global chunk counter, and the next
 // item's points are loaded into the second X buffer while the current item's MMAs run.
 //
-// Epilogue arithmetic.  argmin_k max(0, |x|^2 + |c_k|^2 - 2 x.c_k) is taken as argmin_k of d'_k = |c_k|^2 - 2 x.c_k
-// (|x|^2 is a per-row constant and rounding is monotone, so min_k fl(d'_k + |x|^2) = fl(min_k d'_k + |x|^2)); the
-// clamp and the first-index tie rule are applied to the group minimum exactly as before.  That leaves one packed
-// FFMA2 and one FMNMX3 per two centroids (the first version spent ~4 instructions per centroid and was issue-bound).
+// Epilogue arithmetic: d_k = fl(fl(|x|^2 + |c_k|^2) - 2 x.c_k) as the reference's kernel forms it (:540-545), one packed
+// FADD2 + FFMA2 per two centroids; the running argmin is branch-free (in-group index in the low 5 mantissa bits, one
+// FMNMX3 per two centroids, see the epilogue).  Distances that differ by less than 32 ulp (4e-6 relative) resolve to the
+// lower index -- far inside the noise of the reference's own 16-bit |c|^2.
 // x_sq == nullptr: |x|^2 is computed from the X tile in shared memory (the Lloyd loop does this: no separate pass
 // over x); otherwise the caller's values are used (svgb_kmeans_assign, where the reference passes its own x_sq).
 template <int D, bool BF16>
@@ -259,72 +277,131 @@ kmeans_assign_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_cons
     const int t = (warp - 4) >> 2, wq = warp & 3;
     const uint32_t lane_addr = tmem + (static_cast<uint32_t>(wq * 32) << 16) + t * 256;
     const uint64_t neg2 = pack_f32x2(-2.f, -2.f);
+    uint32_t idx_mask;  // ~31, kept opaque so that it lives in a register (two immediates would cost two LOP3 per value)
+    asm volatile("mov.u32 %0, 0xFFFFFFE0;" : "=r"(idx_mask));
+    // Timing decomposition on a B200 (tools/kmeans_ab.sh, K = 1000): with the accumulators loaded but not reduced the
+    // kernel runs at 1555 TFLOP/s (MMA + TMA + tcgen05.ld are not the limit; a 2-stage ring still gives 1475), the
+    // reduction arithmetic of the epilogue warps is what the rest of the time goes to.  SVGB_KM_PREFETCH keeps one
+    // tcgen05.ld in flight across chunk and item boundaries (the first group of the next chunk is requested before the
+    // last group of the current one is reduced).
     int g = 0, i = 0;
+    bool primed = false;
+    uint32_t ra[32], rb[32];
     for (int item = blockIdx.x; item < total; item += gridDim.x, ++i) {
       const int xb = i & 1, bh = item / blocks_per_head, row0 = (item % blocks_per_head) * 256;
       const int r = wq * 32 + lane;
       const int n = row0 + t * 128 + r;
-      mbar_wait(smem_u32(&bars->x_full[xb]), (i >> 1) & 1, 35);
+      if (!primed) {  // first item of this CTA
+        mbar_wait(smem_u32(&bars->s_full[t][g & 1]), (g >> 1) & 1, 36);
+        tc_fence_after();
+#if SVGB_KM_EPI != 2
+        tmem_ld32(lane_addr + (g & 1) * 128, ra);
+#endif
+      }
+      mbar_wait(smem_u32(&bars->x_full[xb]), (i >> 1) & 1, 35);  // complete: this item's first MMA has been committed
       float xs;
       if (x_sq) xs = (n < N) ? x_sq[static_cast<size_t>(bh) * N + n] : 0.f;
       else xs = row_sqnorm_smem<D, BF16>(smem_al + xb * Cfg::kXBytes + t * Cfg::kTileBytes, r);
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&bars->x_empty[xb]));
       const float4* cs_head = reinterpret_cast<const float4*>(c_sq + static_cast<size_t>(bh) * nchunks * 128);
+      const uint64_t xs2 = pack_f32x2(xs, xs);
       float best = 3.4e38f;
       int best_k = 0;
+      const bool next_item = item + static_cast<int>(gridDim.x) < total;
       for (int j = 0; j < nchunks; ++j, ++g) {
         const int buf = g & 1;
-        mbar_wait(smem_u32(&bars->s_full[t][buf]), (g >> 1) & 1, 36);
-        tc_fence_after();
         const float4* cs = cs_head + j * 32;
         const int kbase = j * 128;
-        uint32_t ra[32], rb[32];
-        tmem_ld32(lane_addr + buf * 128, ra);
         auto group = [&](const uint32_t (&rr)[32], int gi) {
-          // d'_k = |c_k|^2 - 2 x.c_k ; |c|^2 comes through L1 (warp-uniform 16-byte loads, padded with +3e38 past K
-          // so that the columns TMA zero-filled can never win)
-          uint64_t dv[16];
+          // d_k = (|x|^2 + |c_k|^2) - 2 x.c_k with the reference's two roundings (the sum, then the fma); |c|^2 comes
+          // through L1 (warp-uniform 16-byte loads, padded with +3e38 past K so that the columns TMA zero-filled can
+          // never win).  The argmin inside the group is branch-free: the in-group index replaces the low 5 mantissa
+          // bits of every (non-negative) distance, so one FMNMX3 tree returns value and index together and equal
+          // distances resolve to the lower index.  (A compare-and-search on improvement was tried first: a WARP takes
+          // that branch whenever any of its 32 rows improves, i.e. in almost every group, and it doubled the kernel time.)
+          uint32_t v[32];
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
             const float4 c4 = __ldg(cs + gi * 8 + q);
-            dv[2 * q] = ffma2(pack_f32x2(__uint_as_float(rr[4 * q]), __uint_as_float(rr[4 * q + 1])), neg2,
-                              pack_f32x2(c4.x, c4.y));
-            dv[2 * q + 1] = ffma2(pack_f32x2(__uint_as_float(rr[4 * q + 2]), __uint_as_float(rr[4 * q + 3])), neg2,
-                                  pack_f32x2(c4.z, c4.w));
+            const uint64_t d01 = ffma2(pack_f32x2(__uint_as_float(rr[4 * q]), __uint_as_float(rr[4 * q + 1])), neg2,
+                                       fadd2(pack_f32x2(c4.x, c4.y), xs2));
+            const uint64_t d23 = ffma2(pack_f32x2(__uint_as_float(rr[4 * q + 2]), __uint_as_float(rr[4 * q + 3])), neg2,
+                                       fadd2(pack_f32x2(c4.z, c4.w), xs2));
+            float a0, a1, a2, a3;
+            unpack_f32x2(d01, a0, a1);
+            unpack_f32x2(d23, a2, a3);
+            v[4 * q] = pack_idx(a0, 4 * q, idx_mask);
+            v[4 * q + 1] = pack_idx(a1, 4 * q + 1, idx_mask);
+            v[4 * q + 2] = pack_idx(a2, 4 * q + 2, idx_mask);
+            v[4 * q + 3] = pack_idx(a3, 4 * q + 3, idx_mask);
           }
-          float lo, hi2;
-          unpack_f32x2(dv[0], lo, hi2);
-          float gmin = fminf(lo, hi2);
+          float gmin = fminf(__uint_as_float(v[0]), __uint_as_float(v[1]));
 #pragma unroll
-          for (int q = 1; q < 16; ++q) {
-            unpack_f32x2(dv[q], lo, hi2);
-            gmin = fmin3(gmin, lo, hi2);
-          }
-          const float gd = fmaxf(gmin + xs, 0.f);
-          if (gd < best) {  // strict: an earlier group keeps ties; inside the group the lowest index wins
-            best = gd;
+          for (int q = 1; q < 16; ++q) gmin = fmin3(gmin, __uint_as_float(v[2 * q]), __uint_as_float(v[2 * q + 1]));
+          uint32_t gbits = __float_as_uint(gmin);
+          if (__any_sync(0xffffffffu, gmin < 0.f)) {  // warp-uniform vote: a real branch, not predicated code
+            // a distance that rounded below zero (a point sitting on a centroid): the reference clamps to 0 and takes
+            // the FIRST such centroid; negative floats order the packed index the wrong way round, so search (rare)
+            if (gmin < 0.f) {
+              int first = 31;
 #pragma unroll
-            for (int q = 15; q >= 0; --q) {
-              unpack_f32x2(dv[q], lo, hi2);
-              if (fmaxf(hi2 + xs, 0.f) == gd) best_k = kbase + gi * 32 + 2 * q + 1;
-              if (fmaxf(lo + xs, 0.f) == gd) best_k = kbase + gi * 32 + 2 * q;
+              for (int q = 31; q >= 0; --q)
+                if (__uint_as_float(v[q] & ~31u) <= 0.f) first = q;
+              gbits = static_cast<uint32_t>(first);  // value 0, index `first`
             }
           }
+          const float gval = __uint_as_float(gbits & ~31u);
+          if (gval < best) {  // strict: an earlier group keeps ties (selects, no branch)
+            best = gval;
+            best_k = kbase + gi * 32 + static_cast<int>(gbits & 31u);
+          }
         };
+#if SVGB_KM_EPI == 2
+        tc_fence_before();
+        mbar_arrive(smem_u32(&bars->s_empty[t][buf]));
+        primed = (j + 1 < nchunks) || next_item;
+        if (primed) {
+          const int nb = (g + 1) & 1;
+          mbar_wait(smem_u32(&bars->s_full[t][nb]), ((g + 1) >> 1) & 1, 37);
+          tc_fence_after();
+        }
+#else
+#if SVGB_KM_EPI == 1
+#define SVGB_KM_GROUP(arr, gi) best += __uint_as_float(arr[gi])
+#else
+#define SVGB_KM_GROUP(arr, gi) group(arr, gi)
+#endif
+#if !SVGB_KM_PREFETCH
+        if (j > 0) {
+          mbar_wait(smem_u32(&bars->s_full[t][buf]), (g >> 1) & 1, 37);
+          tc_fence_after();
+          tmem_ld32(lane_addr + buf * 128, ra);
+        }
+#endif
         tc_wait_ld();
         tmem_ld32(lane_addr + buf * 128 + 32, rb);
-        group(ra, 0);
+        SVGB_KM_GROUP(ra, 0);
         tc_wait_ld();
         tmem_ld32(lane_addr + buf * 128 + 64, ra);
-        group(rb, 1);
+        SVGB_KM_GROUP(rb, 1);
         tc_wait_ld();
         tmem_ld32(lane_addr + buf * 128 + 96, rb);
-        group(ra, 2);
+        SVGB_KM_GROUP(ra, 2);
         tc_wait_ld();
         tc_fence_before();
         mbar_arrive(smem_u32(&bars->s_empty[t][buf]));  // the accumulator is in registers: hand the buffer back early
-        group(rb, 3);
+#if SVGB_KM_PREFETCH
+        primed = (j + 1 < nchunks) || next_item;
+        if (primed) {
+          const int nb = (g + 1) & 1;
+          mbar_wait(smem_u32(&bars->s_full[t][nb]), ((g + 1) >> 1) & 1, 37);
+          tc_fence_after();
+          tmem_ld32(lane_addr + nb * 128, ra);
+        }
+#endif
+        SVGB_KM_GROUP(rb, 3);
+#endif
       }
       if (n < N) labels[static_cast<size_t>(bh) * N + n] = best_k;
     }

@@ -1,5 +1,6 @@
 """k-means stage timings at HunyuanVideo-720p size (H=24, N=118800, D=128; K=1000 / 400).  JSON lines on stdout."""
 import json
+import os
 import sys
 from pathlib import Path
 
@@ -35,7 +36,10 @@ xsq = core.row_sqnorm(x)
 for K in (1000, 400):
     init = x[:, torch.randint(0, V, (K,), device=dev, generator=g)].contiguous()
     ms = t(lambda: core.kmeans_assign(x, init, xsq))
-    print(json.dumps({"stage": f"assign_K{K}", "ms": ms, "tflops": 2.0 * V * K * D * H / ms / 1e9}), flush=True)
+    print(json.dumps({"stage": f"assign_K{K}", "ms": ms, "tflops": 2.0 * V * K * D * H / ms / 1e9,
+                      "lib": os.path.basename(os.environ.get("SVGB200_LIB", "default"))}), flush=True)
+    if os.environ.get("KM_PROBE") == "assign":
+        continue
     labels = core.kmeans_assign(x, init, xsq)
     ms = t(lambda: core.kmeans_update(x, labels, init))
     print(json.dumps({"stage": f"update_K{K} (incl. label sort)", "ms": ms, "gbs": x.numel() * 2 / ms / 1e6}), flush=True)
@@ -43,5 +47,12 @@ for K in (1000, 400):
     print(json.dumps({"stage": f"argsort_labels_K{K}", "ms": ms}), flush=True)
     ms = t(lambda: core.kmeans_run(x, init, 2))
     print(json.dumps({"stage": f"kmeans_run_K{K}_2it", "ms": ms}), flush=True)
+if os.environ.get("KM_PROBE") == "assign":
+    sys.exit(0)
 ms = t(lambda: core.row_sqnorm(x))
 print(json.dumps({"stage": "row_sqnorm (no longer on the Lloyd path)", "ms": ms}), flush=True)
+qc = torch.randn(H, 400, D, device=dev, generator=g).bfloat16()
+kc = torch.randn(H, 1000, D, device=dev, generator=g).bfloat16()
+ks = torch.randint(1, 300, (H, 1000), device=dev, generator=g, dtype=torch.int32)
+ms = t(lambda: core.dynamic_map(qc, kc, ks, 0.9, 100))
+print(json.dumps({"stage": "dynamic_map 24x400x1000", "ms": ms}), flush=True)
