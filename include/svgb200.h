@@ -179,7 +179,8 @@ int svgb_kmeans_run(const void* x, const void* init_centroids, int BH, int N, in
  * (x_head_stride elements between heads, 0 = N*D; rows stay D apart) so the video part of [H, S, D] is clustered in
  * place (the reference's `[:, :, :-context_length]` slice + `.contiguous()`), and perm_out (optional, int32 [BH,N])
  * receives the stable argsort of the returned labels -- what the reference recomputes with torch.argsort in
- * permute_tensor_by_labels (svg/kmeans_utils.py:829-838) -- for free: the last centroid update already built it. */
+ * permute_tensor_by_labels_triton (svg/kernels/triton/permute.py:113; hyvideo/attention.py:651-652) -- for free: the
+ * last centroid update already built it. */
 int svgb_kmeans_run_sorted(const void* x, long long x_head_stride, const void* init_centroids, int BH, int N, int K,
                            int D, int dtype, int max_iters, float tol, int32_t* labels, void* centroids_out,
                            int32_t* counts, int32_t* n_iter_out, int32_t* perm_out, void* ws, size_t ws_bytes,

@@ -67,7 +67,7 @@ def batch_kmeans_Euclid(x, n_clusters, max_iters=100, tol=1e-4, init_centroids=N
 
 def batch_kmeans_Euclid_sorted(x, n_clusters, max_iters=100, tol=1e-4, init_centroids=None):
     """batch_kmeans_Euclid for the SAP cores: same clustering, labels stay int32 and the stable argsort of the labels
-    comes back as a fifth value (the reference recomputes it: permute_tensor_by_labels, svg/kmeans_utils.py:829-838)."""
+    comes back as a fifth value (the reference recomputes it with torch.argsort: permute_tensor_by_labels_triton, svg/kernels/triton/permute.py:83-128)."""
     B, N, D = x.shape
     if init_centroids is None:
         idx = torch.randint(0, N, (B, n_clusters), device=x.device)  # GPU generator, like :708

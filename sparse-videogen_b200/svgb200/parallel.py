@@ -9,6 +9,7 @@ head's attention finishes — the transfer of head i overlaps the attention of h
 """
 from __future__ import annotations
 
+import os
 from typing import Callable, Optional
 
 import torch
@@ -36,11 +37,13 @@ class HeadParallel:
     def streams(self, device, compute_streams: int = 2):
         """(communication stream, compute side streams), created on first use."""
         if self._comm_stream is None:
-            # HIGH priority: the attention kernel fills every SM (1 CTA / SM, the whole register file), so an NCCL
-            # kernel on a default-priority stream only gets SMs when the attention grid drains -- the N = 8 timeline
-            # of round 2 showed all three per-head all-gathers running back to back AFTER the last head (1.36 ms
-            # exposed of 8.8).  With priority the block scheduler hands freed SMs to the waiting NCCL CTAs first.
-            self._comm_stream = torch.cuda.Stream(device=device, priority=-1)
+            # High priority so that NCCL CTAs are scheduled ahead of queued attention CTAs when SMs free up (the attention
+            # kernel fills every SM: 1 CTA / SM, the whole register file).  Measured at N = 8 in one session
+            # (profiles/r02_hp_priority_ab.txt): 6579 / 6417 TFLOP/s with priority -1, 6430 / 6420 with the default --
+            # no measurable difference; what is exposed is the all-gather of the LAST head (~0.9 ms of 8.0), which has
+            # no compute left to hide behind.
+            prio = int(os.environ.get("SVGB_HP_COMM_PRIORITY", "-1"))  # 0 = default priority (A/B switch)
+            self._comm_stream = torch.cuda.Stream(device=device, priority=prio)
             self._compute_streams = [torch.cuda.Stream(device=device) for _ in range(max(1, compute_streams))]
         return self._comm_stream, self._compute_streams
 
