@@ -177,7 +177,7 @@ struct AttnArgs {
   const int* q_index;       // optional [S]: query position used by the element mask (sampled rows)
   int out_f32;              // 1: o is fp32 (used for split-KV partials)
   int softmax_shared;       // 1: both softmax warpgroups share one tile at a time (plans with narrow chunks)
-  int sub_mode;             // experimental sub-chunk pipeline (SVGB_ATTN_SUB): 0 off, 1 on, 2 on + deferred P release
+  int sub_mode;             // opt-in sub-chunk pipeline (SVGB_ATTN_SUB=1): 0 off, 1 on
   int arrival_order;        // two-tile items: serve the tiles' MMAs in P-arrival order (SVGB_ATTN_ORDER=1)
   // FP8 (e4m3) inputs: per-head dequantisation scales [BH]; s_q * s_k multiplies the logits, s_v the
   // output.  NULL for 16-bit inputs.

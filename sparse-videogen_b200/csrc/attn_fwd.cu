@@ -449,7 +449,7 @@ static int launch_attn(const CUtensorMap& qm, const CUtensorMap& km, const CUten
   }
   if constexpr (DT != DT_E4M3 && D == 128) {
     // experimental sub-chunk pipeline (attn_kernel.cuh, kSub): opt-in until it is validated on the GPU
-    static const int sub = [] { const char* e = getenv("SVGB_ATTN_SUB"); return (e && (e[0] == '1' || e[0] == '2')) ? e[0] - '0' : 0; }();
+    static const int sub = [] { const char* e = getenv("SVGB_ATTN_SUB"); return (e && e[0] == '1') ? 1 : 0; }();
     if (sub && !args.softmax_shared && !args.items2) {
       auto kern = attn_fwd_kernel<D, DT, false, true>;
       SVGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));

@@ -813,19 +813,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
       if constexpr (kSub) {
       // ---- sub-chunk pipeline: two 64-column online-softmax steps per chunk (see the MMA issuer)
       int nsub = 0;  // PV groups issued into O_t so far == sub-steps finished
-      // sub_mode 2 (NOT yet run on a GPU): the tcgen05.wait::st + arrival of sub-step n is deferred until the loads and
-      // the row max of sub-step n+1 are done, so the store latency (~200 cycles) leaves the softmax thread's path
-      const bool defer = args.sub_mode == 2;
-      bool pending = false;
-      uint32_t pend_bar = 0;
-      auto flush_pending = [&]() {
-        if (pending) {
-          tc_wait_st();
-          tc_fence_before();
-          mbar_arrive(pend_bar);
-          pending = false;
-        }
-      };
       for (int j = 0; j < nchunks; ++j) {
         const int kv0 = ch.x;
         const int valid = chunk_valid(ch.y);
@@ -876,7 +863,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
                 m_used = m_new;
               }
               SVGB_TRACE(t, nsub, 3);
-              flush_pending();  // P of the previous sub-step: its stores landed while this one loaded and reduced
               if (nsub > 0 && __any_sync(0xffffffffu, alpha != 1.f)) {
                 // every PV group issued so far must have landed in O_t before it is rescaled
                 mbar_wait(smem_u32(&bars->sub_pv[t]), (nsub - 1) & 1, 12);
@@ -928,21 +914,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
             if (!elem && vh == 64) half_body(std::true_type{});
             else half_body(std::false_type{});
             l_run += rs;
-            if (!defer) tc_wait_st();
+            tc_wait_st();
             SVGB_TRACE(t, nsub, 5);
           }
-          if (defer) {
-            flush_pending();  // only still pending when this half was empty (nh == 0)
-            pending = true;
-            pend_bar = smem_u32(&bars->sub_p[t][h]);
-          } else {
-            tc_fence_before();
-            mbar_arrive(smem_u32(&bars->sub_p[t][h]));
-            SVGB_TRACE(t, nsub, 6);
-          }
+          tc_fence_before();
+          mbar_arrive(smem_u32(&bars->sub_p[t][h]));
+          SVGB_TRACE(t, nsub, 6);
         }
       }
-      flush_pending();
       } else
       for (int j = 0; j < my_n; ++j) {
         const int kv0 = ch.x;
