@@ -1,4 +1,4 @@
-"""Host logic of the SVG2 dispatcher on the CPU (no GPU, no CUDA library).
+"""Host logic of the SVG2 and SVG1 dispatchers on the CPU (no GPU, no CUDA library).
 
 `SAPCore.sparse_core` (svgb200/models/common.py; reference: svg/models/hyvideo/attention.py:555-804, wan :375-559) is
 host code around six device operators.  Here those operators are replaced by oracle-backed stand-ins -- test
@@ -155,3 +155,84 @@ def test_wan_sap_core_host_logic(cpu_ops):
     assert all(r["shape"] == (H, S, D) for r in runs)  # no text: the whole sequence, as it is
     assert sap.last["dynamic_map"].shape == (H, 3, 5)
     torch.testing.assert_close(o.float(), _reference(q, k, v, sap, 0, 0), rtol=3e-2, atol=2e-2)
+
+
+# ------------------------------------------------------------------------------------------------ SVG1 dispatcher
+@pytest.fixture
+def cpu_ops_svg1(monkeypatch):
+    """Device operators of the SVG1 core -> oracle stand-ins (band plan, profiling, placement, attention)."""
+    from oracle import attention as oa
+    from svgb200 import core
+
+    class _Band:
+        def __init__(self, mode, m0, m1, m2, S):
+            self.mode, self.m0, self.m1, self.m2, self.S = mode, m0, m1, m2, S
+
+    calls = {"attn": [], "placement": []}
+
+    def plan_band(mode, m0, m1, m2, BH, S, device):
+        return _Band(mode, m0, m1, m2, S)
+
+    def sample_mse(q, k, v, rows, layout, ctx, F, P):
+        name = {0: "hy", 1: "wan"}[layout]
+        masks = [oa.profiling_mask_rows(m, rows, name, ctx, F, P) for m in ("spatial", "temporal")]
+        return oa.sample_mse(q[None], k[None], v[None], rows, masks)[:, 0]
+
+    def head_placement(ins, outs, best_mask_idx, ctx, F, P, *, text_first=False, inverse=False):
+        calls["placement"].append({"n": len(ins), "inverse": inverse, "text_first": text_first})
+        idx = best_mask_idx.reshape(-1).numpy()
+        for src, dst in zip(ins, outs):
+            dst.copy_(ol.head_placement(src[0], idx, ctx, F, P, text_first=text_first, inverse=inverse)[None])
+        return outs
+
+    def plan_varblock(bm, row, col, S, **_):  # dense fall-back = one all-true block
+        return ("dense", bm, row, col)
+
+    def attn_fwd(q, k, v, plan, **_):
+        if isinstance(plan, tuple):
+            calls["attn"].append("dense")
+            return oa.masked_attention_bhsd(q[0], k[0], v[0], None)[None].to(q.dtype)
+        calls["attn"].append("band")
+        fn = oa.generic_mask_fn(plan.mode, plan.m0, plan.m1, plan.m2)
+        return oa.masked_attention_bhsd(q[0], k[0], v[0], fn)[None].to(q.dtype)
+
+    for name, fn in (("plan_band", plan_band), ("sample_mse", sample_mse), ("head_placement", head_placement),
+                     ("plan_varblock", plan_varblock), ("attn_fwd", attn_fwd)):
+        monkeypatch.setattr(core, name, fn)
+    return calls
+
+
+def test_hunyuan_svg1_core_host_logic(cpu_ops_svg1):
+    from oracle import attention as oa
+    from svgb200.models import hyvideo as hy
+
+    g = torch.Generator().manual_seed(9)
+    H, F, P, ctx, plen, D = 3, 4, 128, 40, 17, 64
+    S = ctx + F * P
+    q, k, v = (torch.randn(1, H, S, D, generator=g).to(torch.bfloat16) for _ in range(3))
+    coreobj = hy.HunyuanSVG1Core(ctx, plen, F, P, H, D, 0.4, torch.device("cpu"), num_sampled_rows=16,
+                                 sample_mse_max_row=300, first_layers_fp=1, first_times_fp=900, layer_idx=2)
+    rows = torch.randint(0, 300, (16,), generator=g)
+    o = coreobj.sparse_core(q, k, v, sampled_rows=rows)
+    assert cpu_ops_svg1["attn"] == ["band"]
+    # one placement call for Q, K, V together, one inverse call for the output
+    assert [(c["n"], c["inverse"]) for c in cpu_ops_svg1["placement"]] == [(3, False), (1, True)]
+    masks = [oa.profiling_mask_rows(mn, rows, "hy", ctx, F, P) for mn in ("spatial", "temporal")]
+    best = oa.sample_mse(q, k, v, rows, masks).bfloat16().argmin(0).view(-1)
+    mul = oa.sparsity_to_width(0.4, ctx, F, P)
+    mod = oa.hy_mask_mod(ctx, plen, F, P, mul)
+    qp, kp, vp = (ol.head_placement(t[0], best.numpy(), ctx, F, P) for t in (q, k, v))
+    ref = ol.head_placement(oa.masked_attention_bhsd(qp, kp, vp, mod).bfloat16(), best.numpy(), ctx, F, P, inverse=True)
+    torch.testing.assert_close(o[0].float(), ref.float(), rtol=3e-2, atol=2e-2)
+
+    # dispatcher (hyvideo/attention.py:473-524): dense for the first layers and for the early (large) timesteps
+    cpu_ops_svg1["attn"].clear()
+    coreobj.attention_core_logic(q, k, v, timestep=torch.tensor([950]))
+    assert cpu_ops_svg1["attn"] == ["dense"]
+    cpu_ops_svg1["attn"].clear()
+    coreobj.attention_core_logic(q, k, v, timestep=torch.tensor([500]))
+    assert cpu_ops_svg1["attn"] == ["band"]
+    coreobj.layer_idx = 0
+    cpu_ops_svg1["attn"].clear()
+    coreobj.attention_core_logic(q, k, v, timestep=torch.tensor([500]))
+    assert cpu_ops_svg1["attn"] == ["dense"]
