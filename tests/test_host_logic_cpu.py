@@ -174,6 +174,9 @@ def cpu_ops_svg1(monkeypatch):
         return _Band(mode, m0, m1, m2, S)
 
     def sample_mse(q, k, v, rows, layout, ctx, F, P):
+        if layout == 2:  # CogVideoX; rows without keys give 0 in the kernel, NaN in the naive formulation
+            masks = [oa.profiling_mask_rows_cog(m, rows, ctx, F, P) for m in ("spatial", "temporal")]
+            return torch.nan_to_num(oa.sample_mse(q[None], k[None], v[None], rows, masks)[:, 0], nan=0.0)
         name = {0: "hy", 1: "wan"}[layout]
         masks = [oa.profiling_mask_rows(m, rows, name, ctx, F, P) for m in ("spatial", "temporal")]
         return oa.sample_mse(q[None], k[None], v[None], rows, masks)[:, 0]
@@ -236,3 +239,37 @@ def test_hunyuan_svg1_core_host_logic(cpu_ops_svg1):
     cpu_ops_svg1["attn"].clear()
     coreobj.attention_core_logic(q, k, v, timestep=torch.tensor([500]))
     assert cpu_ops_svg1["attn"] == ["dense"]
+
+
+def test_cog_svg1_core_host_logic(cpu_ops_svg1):
+    """CogVideoX: text FIRST, rows sampled over the whole sequence, a sampled text row makes every head temporal (the
+    reference's NaN argmin, cog/utils.py:76-86 + cog/attention.py:124-160), scaled dense thresholds (:172-175)."""
+    from oracle import attention as oa
+    from svgb200.models import cog
+
+    g = torch.Generator().manual_seed(12)
+    H, F, P, ctx, D = 2, 3, 128, 26, 64
+    S = ctx + F * P
+    q, k, v = (torch.randn(1, H, S, D, generator=g).to(torch.bfloat16) for _ in range(3))
+    c = cog.CogSVG1Core(ctx, F, P, H, D, 0.4, torch.device("cpu"), num_sampled_rows=12, first_layers_fp=0.05,
+                        first_times_fp=0.2, layer_idx=10)
+    for rows in (torch.randint(ctx, S, (12,), generator=g),
+                 torch.cat([torch.tensor([5]), torch.randint(ctx, S, (11,), generator=g)])):
+        cpu_ops_svg1["placement"].clear()
+        o = c.sparse_core(q, k, v, sampled_rows=rows)
+        assert all(call["text_first"] for call in cpu_ops_svg1["placement"])
+        masks = [oa.profiling_mask_rows_cog(mn, rows, ctx, F, P) for mn in ("spatial", "temporal")]
+        best = torch.argmin(oa.sample_mse(q, k, v, rows, masks).bfloat16(), dim=0).view(-1)
+        if bool((rows < ctx).any()):
+            assert (best == 1).all()
+        mod = oa.cog_mask_mod(ctx, F, P, oa.sparsity_to_width(0.4, ctx, F, P))
+        qp, kp, vp = (ol.head_placement(t[0], best.numpy(), ctx, F, P, text_first=True) for t in (q, k, v))
+        ref = ol.head_placement(oa.masked_attention_bhsd(qp, kp, vp, mod).bfloat16(), best.numpy(), ctx, F, P,
+                                text_first=True, inverse=True)
+        torch.testing.assert_close(o[0].float(), ref.float(), rtol=3e-2, atol=2e-2)
+    # dense while layer_idx < 42 * first_layers_fp (= 2.1) or timestep > 1000 * (1 - first_times_fp) (= 800)
+    for layer, ts, want in ((10, 700.0, "band"), (10, 900.0, "dense"), (2, 700.0, "dense"), (3, 700.0, "band")):
+        c.layer_idx = layer
+        cpu_ops_svg1["attn"].clear()
+        c.attention_core_logic(q, k, v, torch.tensor([ts]))
+        assert cpu_ops_svg1["attn"] == [want], (layer, ts)
