@@ -273,3 +273,23 @@ def test_cog_svg1_core_host_logic(cpu_ops_svg1):
         cpu_ops_svg1["attn"].clear()
         c.attention_core_logic(q, k, v, torch.tensor([ts]))
         assert cpu_ops_svg1["attn"] == [want], (layer, ts)
+
+
+def test_wan_svg1_core_host_logic(cpu_ops_svg1):
+    """Wan 2.1 (no text; first-frame sink + band, wan/utils.py:30-46; profiling layout 1)."""
+    from oracle import attention as oa
+    from svgb200.models import wan
+
+    g = torch.Generator().manual_seed(13)
+    H, F, P, D = 2, 4, 128, 64
+    S = F * P
+    q, k, v = (torch.randn(1, H, S, D, generator=g).to(torch.bfloat16) for _ in range(3))
+    c = wan.WanSVG1Core(F, P, H, D, 0.5, torch.device("cpu"), num_sampled_rows=16, sample_mse_max_row=400)
+    rows = torch.randint(0, 400, (16,), generator=g)
+    o = c.sparse_core(q, k, v, sampled_rows=rows)
+    masks = [oa.profiling_mask_rows(mn, rows, "wan", 0, F, P) for mn in ("spatial", "temporal")]
+    best = oa.sample_mse(q, k, v, rows, masks).bfloat16().argmin(0).view(-1)
+    mod = oa.wan_mask_mod(F, P, oa.sparsity_to_width(0.5, 0, F, P))
+    qp, kp, vp = (ol.head_placement(t[0], best.numpy(), 0, F, P) for t in (q, k, v))
+    ref = ol.head_placement(oa.masked_attention_bhsd(qp, kp, vp, mod).bfloat16(), best.numpy(), 0, F, P, inverse=True)
+    torch.testing.assert_close(o[0].float(), ref.float(), rtol=3e-2, atol=2e-2)
